@@ -1,0 +1,1176 @@
+// C ABI (include/dfr.h) of the B200-native DiffDFSPH step: context management, HBM layout,
+// launch sequences.  Host code here only enqueues kernels; the step itself (solver loops, CFL,
+// rigid update, chain rule) runs on the device (see dfr_kernels.cuh, dfr_rigid.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dfr.h"
+#include "dfr_kernels.cuh"
+#include "dfr_rigid.cuh"
+
+using namespace dfr;
+
+namespace {
+
+struct HostBody {
+  std::vector<double> x_local;  // n*3
+  int64_t n = 0;
+  int dynamic = 0;
+  double density = 1000.0;
+  double pos[3], q[4];
+  double init_v[3] = {0, 0, 0}, init_w[3] = {0, 0, 0};
+  int p_begin = 0;  // slice in the concatenated (unsorted) boundary layout
+  int blk_begin = 0, blk_count = 0;  // accumulator rows of the boundary-side kernel
+  BodyDev dev0;     // initial device record (reset() uploads it)
+};
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct dfr_context {
+  dfr_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  bool finalized = false;
+
+  Params P;
+  DevBuf<Params> dP;
+  DevBuf<StepState> dSt;
+  StepState *hSt = nullptr;  // pinned mirror
+
+  // host-side scene description
+  std::vector<double> h_fx, h_fv;
+  int64_t nf0 = 0, nf_cap = 0;
+  std::vector<HostBody> bodies;
+  int n_static_p = 0, n_dyn_p = 0, n_b = 0, dyn_begin = 0;
+  bool has_emitters = false;
+
+  // fluid, cell order, double buffered where the per-step re-sort needs it
+  DevBuf<double4> pos[2], vel[2];
+  DevBuf<double> kappa[2], kappav[2];
+  DevBuf<int> pid[2], pstate[2];
+  int cur = 0, vcur = 0;  // current buffer of (pos,kappa,kappav,pid,pstate) / of vel
+  DevBuf<double4> acc, sgp, normal;
+  DevBuf<double> density, factor, dadv, stiff, partials;
+  // initial state in HBM (id order) restored by dfr_reset
+  DevBuf<double4> pos_init, vel_init;
+  DevBuf<double> kappa_init, kappav_init;
+
+  // boundary particles: [static (cell order) | dynamic (body order)]
+  DevBuf<double4> bpos, bvel, bx0, bpos_tmp, bx0_tmp;
+  DevBuf<int> bbody, borig, bbody_tmp, borig_tmp;
+  DevBuf<double> bvol;
+  std::vector<int> h_borig;  // after the static sort
+
+  DevBuf<BodyDev> dBodies;
+  DevBuf<MgrBlock> dMgr;
+  DevBuf<double> acc_rows;
+  DevBuf<int> blk_body, blk_first;
+  int n_acc_blocks = 0;
+
+  // grids
+  DevBuf<unsigned int> cell_start_f, cell_start_s, cell_start_d, tile_sums;
+  DevBuf<int> cell_of_p, rank_in_cell, sorted_src_f, sorted_src_d, cell_of_b, rank_b;
+  // neighbour lists
+  DevBuf<int> cnt_f, cnt_b, idx_f, idx_b, idx_d;
+  DevBuf<unsigned int> woff_f, woff_b, off_d;
+  unsigned int cap_f = 0, cap_b = 0, cap_d = 0;
+
+  // bookkeeping
+  int spec_div = 1, spec_prs = 2;
+  double device_ms = 0.0;
+  int64_t launches = 0;
+  int launch_nf = 0;
+};
+
+namespace {
+
+int fail(dfr_context *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(c, DFR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+#define LAUNCH(c, kernel, grid, block, ...)                        \
+  do {                                                             \
+    if ((grid) > 0) {                                              \
+      kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+      (c)->launches++;                                             \
+    }                                                              \
+  } while (0)
+
+int scan_u32(dfr_context *c, unsigned int *data, size_t n, unsigned int *total) {
+  const int ntiles = cdiv((int64_t)n, SCAN_TILE);
+  if ((size_t)ntiles > c->tile_sums.n) return fail(c, DFR_ERR_CAPACITY, "scan scratch too small");
+  LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, data, data, c->tile_sums.p, n);
+  LAUNCH(c, k_scan_sums, 1, 1024, c->tile_sums.p, ntiles, total);
+  if (ntiles > 1) LAUNCH(c, k_scan_add, cdiv((int64_t)n, 256), 256, data, c->tile_sums.p, n);
+  return DFR_OK;
+}
+
+void host_body_record(dfr_context *c, HostBody &hb, int p_begin_dev) {
+  // Dynamic3dRigidBody::determineMassProperties (Dynamic3dRigidBody.h:184-198)
+  BodyDev &B = hb.dev0;
+  std::memset(&B, 0, sizeof(B));
+  const double r = c->cfg.particle_radius;
+  const double volume = (4.0 / 3.0 * M_PI) * r * r * r;
+  const double dm = volume * hb.density;
+  double mass = 0.0;
+  double I0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < hb.n; i++) {
+    mass += dm;
+    const double x = hb.x_local[3 * i], y = hb.x_local[3 * i + 1], z = hb.x_local[3 * i + 2];
+    const double rr = x * x + y * y + z * z;
+    const double v[3] = {x, y, z};
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) I0[3 * a + b] += dm * ((a == b ? rr : 0.0) - v[a] * v[b]);
+  }
+  B.dynamic = hb.dynamic;
+  B.animated = 0;
+  B.p_begin = p_begin_dev;
+  B.p_count = (int)hb.n;
+  B.blk_begin = hb.blk_begin;
+  B.blk_count = hb.blk_count;
+  B.mass = mass;
+  B.inv_mass = 1.0 / mass;
+  for (int k = 0; k < 9; k++) B.I0.a[k] = I0[k];
+  B.pos = B.pos0 = mk3(hb.pos[0], hb.pos[1], hb.pos[2]);
+  B.q.w = hb.q[0]; B.q.x = hb.q[1]; B.q.y = hb.q[2]; B.q.z = hb.q[3];
+  B.q0 = B.q;
+  const m33 R = qrot(B.q);
+  B.I = R * B.I0 * transpose(R);
+  B.Iinv = inverse(B.I);
+  B.vel = B.omega = mk3(0, 0, 0);
+  B.init_v = mk3(hb.init_v[0], hb.init_v[1], hb.init_v[2]);
+  B.init_omega = mk3(hb.init_w[0], hb.init_w[1], hb.init_w[2]);
+  // BoundaryModel_Akinci2012::reset (:141-162)
+  B.v_v0 = m33::identity();
+  B.w_w0 = m33::identity();
+}
+
+GridView grid_fluid(dfr_context *c) {
+  GridView g;
+  g.cell_start = c->cell_start_f.p;
+  g.sorted_src = nullptr;
+  g.pos = c->pos[c->cur].p;
+  g.base = 0;
+  return g;
+}
+GridView grid_static(dfr_context *c) {
+  GridView g;
+  g.cell_start = c->cell_start_s.p;
+  g.sorted_src = nullptr;
+  g.pos = c->bpos.p;
+  g.base = 0;
+  return g;
+}
+GridView grid_dyn(dfr_context *c) {
+  GridView g;
+  g.cell_start = c->cell_start_d.p;
+  g.sorted_src = c->sorted_src_d.p;
+  g.pos = c->bpos.p + c->dyn_begin;
+  g.base = c->dyn_begin;
+  return g;
+}
+NbrList list_f(dfr_context *c) {
+  NbrList l;
+  l.cnt = c->cnt_f.p;
+  l.woff = c->woff_f.p;
+  l.idx = c->idx_f.p;
+  return l;
+}
+NbrList list_b(dfr_context *c) {
+  NbrList l;
+  l.cnt = c->cnt_b.p;
+  l.woff = c->woff_b.p;
+  l.idx = c->idx_b.p;
+  return l;
+}
+
+// cell table of the dynamic boundary particles (rebuilt whenever they moved)
+int build_dyn_grid(dfr_context *c) {
+  if (c->n_dyn_p == 0) return DFR_OK;
+  const int nc = c->P.grid.ncells;
+  cudaMemsetAsync(c->cell_start_d.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
+  LAUNCH(c, k_bin_count, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->bpos.p + c->dyn_begin, (const int *)nullptr, c->n_dyn_p,
+         c->cell_start_d.p, c->cell_of_b.p, c->rank_b.p);
+  int rc = scan_u32(c, c->cell_start_d.p, (size_t)nc + 1, nullptr);
+  if (rc) return rc;
+  LAUNCH(c, k_bin_scatter, cdiv(c->n_dyn_p, 128), 128, (const int *)nullptr, c->n_dyn_p, c->cell_start_d.p, c->cell_of_b.p,
+         c->rank_b.p, c->sorted_src_d.p);
+  LAUNCH(c, k_bin_sort_cells, cdiv(nc, 128), 128, c->cell_start_d.p, nc, c->sorted_src_d.p);
+  return DFR_OK;
+}
+
+// CompactNSearch replacement: counting sort of the fluid into cell order + neighbour lists
+int build_neighbors(dfr_context *c) {
+  const int nc = c->P.grid.ncells;
+  const int n = c->launch_nf;
+  const int *nf_ptr = &c->dSt.p->nf;
+  const int a = c->cur, b = 1 - c->cur;
+  cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
+  LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->dP.p, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
+  int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
+  if (rc) return rc;
+  LAUNCH(c, k_bin_scatter, cdiv(n, 128), 128, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p, c->sorted_src_f.p);
+  LAUNCH(c, k_bin_sort_cells, cdiv(nc, 128), 128, c->cell_start_f.p, nc, c->sorted_src_f.p);
+  LAUNCH(c, k_permute_fluid, cdiv(n, 128), 128, c->dSt.p, c->sorted_src_f.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p,
+         c->kappav[a].p, c->pid[a].p, c->pstate[a].p, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p, c->kappav[b].p,
+         c->pid[b].p, c->pstate[b].p);
+  c->cur = b;
+  c->vcur = 1 - c->vcur;
+  rc = build_dyn_grid(c);
+  if (rc) return rc;
+  const int nw = cdiv(n, 32);
+  cudaMemsetAsync(c->woff_f.p, 0, sizeof(unsigned int) * (nw + 1), c->stream);
+  cudaMemsetAsync(c->woff_b.p, 0, sizeof(unsigned int) * (nw + 1), c->stream);
+  LAUNCH(c, k_nbr_count, cdiv(n, 128), 128, c->dP.p, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->woff_f.p, c->woff_b.p);
+  rc = scan_u32(c, c->woff_f.p, (size_t)nw + 1, nullptr);
+  if (rc) return rc;
+  rc = scan_u32(c, c->woff_b.p, (size_t)nw + 1, nullptr);
+  if (rc) return rc;
+  LAUNCH(c, k_nbr_fill, cdiv(n, 128), 128, c->dP.p, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->woff_f.p, c->woff_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
+  if (c->n_dyn_p > 0) {
+    cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
+    LAUNCH(c, k_dnbr_count, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
+    rc = scan_u32(c, c->off_d.p, (size_t)c->n_dyn_p + 1, nullptr);
+    if (rc) return rc;
+    LAUNCH(c, k_dnbr_fill, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
+           c->off_d.p, c->idx_d.p, c->cap_d);
+  }
+  return DFR_OK;
+}
+
+int compute_boundary_volumes(dfr_context *c) {
+  if (c->n_b == 0) return DFR_OK;
+  LAUNCH(c, k_boundary_volume, cdiv(c->n_b, 128), 128, c->dP.p, c->bpos.p, c->n_b, c->n_static_p, grid_static(c), grid_dyn(c),
+         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->bvol.p);
+  LAUNCH(c, k_store_volume, cdiv(c->n_b, 128), 128, c->bpos.p, c->bvol.p, c->n_b);
+  return DFR_OK;
+}
+
+int sync_state(dfr_context *c) {
+  CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->hSt->error_flags) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "neighbour list capacity exceeded (flags %d; used f=%u b=%u d=%u, cap f=%u b=%u d=%u)",
+                  c->hSt->error_flags, c->hSt->list_used_f, c->hSt->list_used_b, c->hSt->list_used_d, c->cap_f, c->cap_b, c->cap_d);
+    return fail(c, DFR_ERR_CAPACITY, buf);
+  }
+  return DFR_OK;
+}
+
+template <bool PRESSURE>
+void launch_boundary_side(dfr_context *c, bool grad, int iter_kernel) {
+  if (c->n_acc_blocks == 0) return;
+  const int g = c->n_acc_blocks, t = BS_WARPS * 32;
+  const int a = c->cur;
+#define BS_ARGS                                                                                                               \
+  c->dP.p, c->dSt.p, c->dBodies.p, c->blk_body.p, c->blk_first.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p,         \
+      c->bx0.p, c->dyn_begin, c->off_d.p, c->idx_d.p, c->stiff.p, c->dadv.p, c->factor.p, c->sgp.p, c->pstate[a].p, iter_kernel, \
+      c->acc_rows.p
+  if (grad) {
+    if (PRESSURE)
+      LAUNCH(c, (k_boundary_side<0, true>), g, t, BS_ARGS);
+    else
+      LAUNCH(c, (k_boundary_side<1, true>), g, t, BS_ARGS);
+  } else {
+    if (PRESSURE)
+      LAUNCH(c, (k_boundary_side<0, false>), g, t, BS_ARGS);
+    else
+      LAUNCH(c, (k_boundary_side<1, false>), g, t, BS_ARGS);
+  }
+#undef BS_ARGS
+}
+
+// divergenceSolve / pressureSolve (TimeStepDiffDFSPH.cpp:770-881 / 654-768).  Iterations are enqueued
+// speculatively; every iteration kernel exits at once when the on-device residual test has closed the
+// solve, and the host looks at the flag only after the speculated batch.
+template <bool PRESSURE>
+int launch_solver(dfr_context *c) {
+  const int n = c->launch_nf, g = cdiv(n, 128);
+  const int a = c->cur;
+  const bool warm = PRESSURE ? c->cfg.use_pressure_warmstart : c->cfg.use_divergence_warmstart;
+  double *kap = PRESSURE ? c->kappa[a].p : c->kappav[a].p;
+#define RHO_ARGS                                                                                                             \
+  c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
+      c->pstate[a].p, kap, c->dadv.p, c->stiff.p, c->partials.p
+#define PUSH_ARGS c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->stiff.p, c->pstate[a].p, kap, warm ? 1 : 0
+  if (warm) {
+    LAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, 128, RHO_ARGS);
+    launch_boundary_side<PRESSURE>(c, false, 0);
+    LAUNCH(c, (k_push<PRESSURE, false>), g, 128, PUSH_ARGS);
+  }
+  LAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, 128, RHO_ARGS);
+  const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
+  int launched = 0;
+  int spec = PRESSURE ? c->spec_prs : c->spec_div;
+  for (;;) {
+    spec = std::max(1, std::min(spec, max_it - launched));
+    for (int it = 0; it < spec; it++) {
+      launch_boundary_side<PRESSURE>(c, true, 1);
+      LAUNCH(c, (k_push<PRESSURE, true>), g, 128, PUSH_ARGS);
+      LAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, 128, RHO_ARGS);
+    }
+    launched += spec;
+    int rc = sync_state(c);
+    if (rc) return rc;
+    const int active = PRESSURE ? c->hSt->prs_active : c->hSt->div_active;
+    if (!active || launched >= max_it) break;
+    spec = 1;
+  }
+  const int used = PRESSURE ? c->hSt->prs_iters : c->hSt->div_iters;
+  if (PRESSURE)
+    c->spec_prs = std::max(used, c->cfg.min_iterations);
+  else
+    c->spec_div = std::max(used, 1);
+#undef RHO_ARGS
+#undef PUSH_ARGS
+  return DFR_OK;
+}
+
+// one SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169)
+int launch_step(dfr_context *c) {
+  const int n = c->launch_nf, g = cdiv(n, 128);
+  LAUNCH(c, k_begin_step, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p);
+  int rc = build_neighbors(c);
+  if (rc) return rc;
+  LAUNCH(c, k_sum_counts, g, 128, c->dSt.p, c->cnt_f.p, c->cnt_b.p);
+  int a = c->cur;
+  LAUNCH(c, k_density_factor, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
+         c->sgp.p);
+  bool scale_kv = false;
+  if (c->cfg.enable_divergence_solver) {
+    rc = launch_solver<false>(c);
+    if (rc) return rc;
+    scale_kv = c->cfg.use_divergence_warmstart != 0;
+  }
+  if (c->cfg.surface_tension_method == 2)
+    LAUNCH(c, k_normals, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, list_f(c), c->density.p, c->normal.p);
+  LAUNCH(c, k_nonpressure, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+         c->density.p, c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
+  c->vcur = 1 - c->vcur;
+  if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
+  LAUNCH(c, k_cfl_finish, 1, 32, c->dP.p, c->dSt.p);
+  rc = launch_solver<true>(c);
+  if (rc) return rc;
+  LAUNCH(c, k_advect_x, g, 128, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->pstate[a].p, c->kappa[a].p,
+         c->cfg.use_pressure_warmstart ? 1 : 0);
+  if (c->P.n_bodies > 0) {
+    LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
+    LAUNCH(c, k_body_update, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p, c->dMgr.p);
+    if (c->n_dyn_p > 0)
+      LAUNCH(c, k_update_boundary_particles, cdiv(c->n_dyn_p, 128), 128, c->dBodies.p, c->bbody.p, c->bx0.p, c->bpos.p, c->bvel.p,
+             c->dyn_begin, c->n_dyn_p, 0);
+  } else {
+    LAUNCH(c, k_body_update, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p, c->dMgr.p);
+  }
+  return DFR_OK;
+}
+
+int reset_device_state(dfr_context *c) {
+  // fluid: initial state back into the current buffers (id order)
+  const size_t n = (size_t)c->nf0;
+  c->cur = 0;
+  c->vcur = 0;
+  if (n) {
+    CU(cudaMemcpyAsync(c->pos[0].p, c->pos_init.p, n * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->vel[0].p, c->vel_init.p, n * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->kappa[0].p, c->kappa_init.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->kappav[0].p, c->kappav_init.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<int> ids(c->nf_cap);
+    for (int64_t i = 0; i < c->nf_cap; i++) ids[i] = (int)i;
+    CU(cudaMemcpyAsync(c->pid[0].p, ids.data(), c->nf_cap * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemsetAsync(c->pstate[0].p, 0, c->nf_cap * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->sgp.p, 0, c->nf_cap * sizeof(double4), c->stream));
+    CU(cudaMemsetAsync(c->acc.p, 0, c->nf_cap * sizeof(double4), c->stream));
+    CU(cudaMemsetAsync(c->density.p, 0, c->nf_cap * sizeof(double), c->stream));
+  }
+  // bodies
+  if (!c->bodies.empty()) {
+    std::vector<BodyDev> hb(c->bodies.size());
+    for (size_t i = 0; i < c->bodies.size(); i++) {
+      host_body_record(c, c->bodies[i], c->bodies[i].dev0.p_begin);
+      hb[i] = c->bodies[i].dev0;
+    }
+    // keep block slices
+    CU(cudaMemcpyAsync(c->dBodies.p, hb.data(), hb.size() * sizeof(BodyDev), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<MgrBlock> mg(c->bodies.size() * c->bodies.size());
+    std::memset(mg.data(), 0, mg.size() * sizeof(MgrBlock));
+    for (size_t R = 0; R < c->bodies.size(); R++) {  // RigidBodyGradientManager::reset (:477-524)
+      mg[R * c->bodies.size() + R].vn_v0 = m33::identity();
+      mg[R * c->bodies.size() + R].wn_w0 = m33::identity();
+    }
+    CU(cudaMemcpyAsync(c->dMgr.p, mg.data(), mg.size() * sizeof(MgrBlock), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->acc_rows.n) CU(cudaMemsetAsync(c->acc_rows.p, 0, c->acc_rows.n * sizeof(double), c->stream));
+  }
+  StepState st;
+  std::memset(&st, 0, sizeof(st));
+  st.h = c->cfg.time_step_size;
+  st.h_step = st.h;
+  st.nf = (int)c->nf0;
+  CU(cudaMemcpyAsync(c->dSt.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *c->hSt = st;
+  // boundary particles in world space (dynamic ones; static never move), psi
+  if (c->n_dyn_p > 0)
+    LAUNCH(c, k_update_boundary_particles, cdiv(c->n_dyn_p, 128), 128, c->dBodies.p, c->bbody.p, c->bx0.p, c->bpos.p, c->bvel.p,
+           c->dyn_begin, c->n_dyn_p, 1);
+  int rc = build_dyn_grid(c);
+  if (rc) return rc;
+  rc = compute_boundary_volumes(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->spec_div = 1;
+  c->spec_prs = std::max(2, c->cfg.min_iterations);
+  c->device_ms = 0.0;
+  c->launches = 0;
+  return DFR_OK;
+}
+
+}  // namespace
+
+template <int R, int C>
+static void put(double *out, const Mat<R, C> &m) {
+  for (int k = 0; k < R * C; k++) out[k] = m.a[k];
+}
+
+// ===============================================================================================
+extern "C" {
+
+void dfr_default_config(dfr_config *cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->particle_radius = 0.025;
+  cfg->density0 = 1000.0;
+  cfg->gravitation[1] = -9.81;
+  cfg->cfl_method = 1;
+  cfg->cfl_factor = 0.5;
+  cfg->cfl_min_time_step = 0.0001;
+  cfg->cfl_max_time_step = 0.005;
+  cfg->time_step_size = 0.001;
+  cfg->min_iterations = 2;
+  cfg->max_iterations = 100;
+  cfg->max_error = 0.01;
+  cfg->max_iterations_v = 100;
+  cfg->max_error_v = 0.1;
+  cfg->enable_divergence_solver = 1;
+  cfg->use_pressure_warmstart = 1;
+  cfg->use_divergence_warmstart = 1;
+  cfg->viscosity_method = 1;
+  cfg->viscosity = 0.01;
+  cfg->surface_tension_method = 0;
+  cfg->surface_tension = 0.05;
+  cfg->gradient_mode = 1;
+  cfg->rigid_body_mode = 0;
+  cfg->optimize_rotation = 1;
+  cfg->rigid_contact_beta = 1.0;
+  cfg->rigid_contact_gamma = 0.7;
+  cfg->rigid_contact_support_radius_factor = 4.0;
+  cfg->target_time = 0.8;
+}
+
+int dfr_create(const dfr_config *cfg, int device, dfr_context **out) {
+  if (!cfg || !out) return DFR_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DFR_ERR_NO_DEVICE;  // no CPU fallback
+  if (device < 0 || device >= ndev) return DFR_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return DFR_ERR_CUDA;
+  dfr_context *c = new dfr_context();
+  c->cfg = *cfg;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+      cudaEventCreate(&c->ev1) != cudaSuccess || cudaMallocHost((void **)&c->hSt, sizeof(StepState)) != cudaSuccess) {
+    delete c;
+    return DFR_ERR_CUDA;
+  }
+  std::memset(c->hSt, 0, sizeof(StepState));
+  *out = c;
+  return DFR_OK;
+}
+
+void dfr_destroy(dfr_context *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < 2; k++) {
+    c->pos[k].free(); c->vel[k].free(); c->kappa[k].free(); c->kappav[k].free(); c->pid[k].free(); c->pstate[k].free();
+  }
+  c->acc.free(); c->sgp.free(); c->normal.free(); c->density.free(); c->factor.free(); c->dadv.free(); c->stiff.free();
+  c->partials.free(); c->pos_init.free(); c->vel_init.free(); c->kappa_init.free(); c->kappav_init.free();
+  c->bpos.free(); c->bvel.free(); c->bx0.free(); c->bpos_tmp.free(); c->bx0_tmp.free(); c->bbody.free(); c->borig.free();
+  c->bbody_tmp.free(); c->borig_tmp.free(); c->bvol.free(); c->dBodies.free(); c->dMgr.free(); c->acc_rows.free();
+  c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
+  c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
+  c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
+  c->woff_f.free(); c->woff_b.free(); c->off_d.free(); c->dP.free(); c->dSt.free();
+  if (c->hSt) cudaFreeHost(c->hSt);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *dfr_last_error(const dfr_context *c) { return c ? c->err.c_str() : "null context"; }
+
+int dfr_set_fluid(dfr_context *c, int64_t n, const double *x, const double *v) {
+  if (!c) return DFR_ERR_INVALID;
+  if (c->finalized) return fail(c, DFR_ERR_STATE, "set_fluid after finalize");
+  if (n < 0 || (n > 0 && !x)) return fail(c, DFR_ERR_INVALID, "bad fluid arrays");
+  c->nf0 = n;
+  c->h_fx.assign(x, x + 3 * n);
+  if (v)
+    c->h_fv.assign(v, v + 3 * n);
+  else
+    c->h_fv.assign(3 * n, 0.0);
+  return DFR_OK;
+}
+
+int dfr_add_body(dfr_context *c, int64_t n, const double *x_local, int is_dynamic, double density, const double position[3],
+                 const double quat_wxyz[4]) {
+  if (!c) return DFR_ERR_INVALID;
+  if (c->finalized) return fail(c, DFR_ERR_STATE, "add_body after finalize");
+  if (n <= 0 || !x_local || !position || !quat_wxyz) return fail(c, DFR_ERR_INVALID, "bad body arrays");
+  if (c->bodies.size() >= 32) return fail(c, DFR_ERR_CAPACITY, "at most 32 rigid bodies per context");
+  HostBody hb;
+  hb.n = n;
+  hb.x_local.assign(x_local, x_local + 3 * n);
+  hb.dynamic = is_dynamic ? 1 : 0;
+  hb.density = density;
+  std::memcpy(hb.pos, position, sizeof(hb.pos));
+  std::memcpy(hb.q, quat_wxyz, sizeof(hb.q));
+  c->bodies.push_back(std::move(hb));
+  return (int)c->bodies.size() - 1;
+}
+
+int dfr_set_init_v_omega(dfr_context *c, int body, const double v0[3], const double omega0[3]) {
+  if (!c || body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
+  HostBody &hb = c->bodies[body];
+  if (v0) std::memcpy(hb.init_v, v0, sizeof(hb.init_v));
+  if (omega0) std::memcpy(hb.init_w, omega0, sizeof(hb.init_w));
+  if (c->finalized) {  // SimulationDataDiffDFSPH::get_init_v_rb is read at every beginStep
+    cudaSetDevice(c->device);
+    hb.dev0.init_v = mk3(hb.init_v[0], hb.init_v[1], hb.init_v[2]);
+    hb.dev0.init_omega = mk3(hb.init_w[0], hb.init_w[1], hb.init_w[2]);
+    BodyDev *d = c->dBodies.p + body;
+    CU(cudaMemcpyAsync(&d->init_v, &hb.dev0.init_v, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(&d->init_omega, &hb.dev0.init_omega, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return DFR_OK;
+}
+
+int dfr_add_emitter(dfr_context *c, int, int, const double *, const double *, double, double, double) {
+  return fail(c, DFR_ERR_INVALID, "emitters are not implemented in the CUDA path yet");
+}
+
+int dfr_finalize(dfr_context *c) {
+  if (!c) return DFR_ERR_INVALID;
+  if (c->finalized) return fail(c, DFR_ERR_STATE, "already finalized");
+  if (c->cfg.use_rigid_contact_solver) return fail(c, DFR_ERR_INVALID, "rigid contact solver not implemented in the CUDA path yet");
+  cudaSetDevice(c->device);
+  const dfr_config &cfg = c->cfg;
+  Params &P = c->P;
+  std::memset(&P, 0, sizeof(P));
+  // ---- kernels & constants (Simulation.cpp:382-386, SPHKernels.h:25-34, FluidModel.cpp:255-275) ----
+  const double hs = 4.0 * cfg.particle_radius;
+  P.support_radius = hs;
+  P.r2 = hs * hs;
+  P.inv_h = 1.0 / hs;
+  const double h3 = hs * hs * hs;
+  P.k_cubic = 8.0 / (M_PI * h3);
+  P.l_cubic = 48.0 / (M_PI * h3);
+  P.W_zero = P.k_cubic;
+  P.coh_k = 32.0 / (M_PI * std::pow(hs, 9.0));
+  P.coh_c = std::pow(hs, 6.0) / 64.0;
+  P.adh_k = 0.007 / std::pow(hs, 3.25);
+  P.particle_radius = cfg.particle_radius;
+  P.density0 = cfg.density0;
+  const double diam = 2.0 * cfg.particle_radius;
+  P.volume = 0.8 * diam * diam * diam;
+  P.mass = P.volume * cfg.density0;
+  P.gx = cfg.gravitation[0]; P.gy = cfg.gravitation[1]; P.gz = cfg.gravitation[2];
+  P.cfl_factor = cfg.cfl_factor; P.cfl_min = cfg.cfl_min_time_step; P.cfl_max = cfg.cfl_max_time_step;
+  P.cfl_method = cfg.cfl_method;
+  P.min_iter = cfg.min_iterations; P.max_iter = cfg.max_iterations; P.max_iter_v = cfg.max_iterations_v;
+  P.max_error = cfg.max_error; P.max_error_v = cfg.max_error_v;
+  P.use_warm_p = cfg.use_pressure_warmstart; P.use_warm_v = cfg.use_divergence_warmstart;
+  P.visc_method = cfg.viscosity_method; P.st_method = cfg.surface_tension_method;
+  P.viscosity = cfg.viscosity; P.viscosity_b = cfg.viscosity_boundary;
+  P.surface_tension = cfg.surface_tension; P.surface_tension_b = cfg.surface_tension_boundary;
+  P.gradient_mode = cfg.gradient_mode; P.rigid_body_mode = cfg.rigid_body_mode; P.optimize_rotation = cfg.optimize_rotation;
+  P.use_manager = cfg.use_rigid_gradient_manager; P.use_contact = cfg.use_rigid_contact_solver;
+  P.target_time = cfg.target_time; P.uniform_acc_time = cfg.uniform_acc_rb_time;
+  P.time_step_size0 = cfg.time_step_size;
+  P.n_bodies = (int)c->bodies.size();
+
+  // ---- boundary layout: static bodies first, then dynamic ----
+  int off = 0;
+  std::vector<int> order;
+  for (size_t i = 0; i < c->bodies.size(); i++)
+    if (!c->bodies[i].dynamic) order.push_back((int)i);
+  c->n_static_p = 0;
+  for (int i : order) {
+    c->bodies[i].p_begin = off;
+    off += (int)c->bodies[i].n;
+  }
+  c->n_static_p = off;
+  c->dyn_begin = off;
+  int ndynb = 0;
+  for (size_t i = 0; i < c->bodies.size(); i++)
+    if (c->bodies[i].dynamic) {
+      c->bodies[i].p_begin = off;
+      off += (int)c->bodies[i].n;
+      order.push_back((int)i);
+      ndynb++;
+    }
+  c->n_b = off;
+  c->n_dyn_p = c->n_b - c->n_static_p;
+  P.n_dyn_bodies = ndynb;
+
+  // ---- world positions on the host (for the bounding box) ----
+  std::vector<double4> h_bpos(c->n_b), h_bx0(c->n_b);
+  std::vector<int> h_bbody(c->n_b), h_borig(c->n_b);
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  auto grow = [&](double x, double y, double z) {
+    lo[0] = std::min(lo[0], x); lo[1] = std::min(lo[1], y); lo[2] = std::min(lo[2], z);
+    hi[0] = std::max(hi[0], x); hi[1] = std::max(hi[1], y); hi[2] = std::max(hi[2], z);
+  };
+  for (size_t bi = 0; bi < c->bodies.size(); bi++) {
+    HostBody &hb = c->bodies[bi];
+    host_body_record(c, hb, hb.p_begin);
+    const m33 R = qrot(hb.dev0.q);
+    for (int64_t j = 0; j < hb.n; j++) {
+      const d3 x0 = mk3(hb.x_local[3 * j], hb.x_local[3 * j + 1], hb.x_local[3 * j + 2]);
+      const d3 x = R * x0 + hb.dev0.pos;
+      const int g = hb.p_begin + (int)j;
+      h_bpos[g] = make_double4(x.x, x.y, x.z, 0.0);
+      h_bx0[g] = make_double4(x0.x, x0.y, x0.z, 0.0);
+      h_bbody[g] = (int)bi;
+      h_borig[g] = g;
+      grow(x.x, x.y, x.z);
+    }
+  }
+  for (int64_t i = 0; i < c->nf0; i++) grow(c->h_fx[3 * i], c->h_fx[3 * i + 1], c->h_fx[3 * i + 2]);
+  if (c->nf0 == 0 && c->n_b == 0) return fail(c, DFR_ERR_INVALID, "empty scene");
+  // ---- grid: cell edge slightly above the support radius, two cells of margin, capped cell count ----
+  double cell = hs * (1.0 + 1.0e-7);
+  const double margin = 2.0;
+  for (;;) {
+    double nx = std::floor((hi[0] - lo[0]) / cell) + 1 + 2 * margin;
+    double ny = std::floor((hi[1] - lo[1]) / cell) + 1 + 2 * margin;
+    double nz = std::floor((hi[2] - lo[2]) / cell) + 1 + 2 * margin;
+    if (nx * ny * nz <= (double)(1 << 26)) {
+      P.grid.nx = (int)nx; P.grid.ny = (int)ny; P.grid.nz = (int)nz;
+      break;
+    }
+    cell *= 1.26;
+  }
+  P.grid.ox = lo[0] - margin * cell; P.grid.oy = lo[1] - margin * cell; P.grid.oz = lo[2] - margin * cell;
+  P.grid.inv_cell = 1.0 / cell;
+  P.grid.ncells = P.grid.nx * P.grid.ny * P.grid.nz;
+
+  // ---- allocations ----
+  c->nf_cap = c->nf0 + std::max(0, cfg.max_emitted_particles);
+  const size_t N = (size_t)std::max<int64_t>(c->nf_cap, 1);
+  c->launch_nf = (int)c->nf0;
+  const int nc = P.grid.ncells;
+  CU(c->dP.alloc(1));
+  CU(c->dSt.alloc(1));
+  for (int k = 0; k < 2; k++) {
+    CU(c->pos[k].alloc(N)); CU(c->vel[k].alloc(N)); CU(c->kappa[k].alloc(N)); CU(c->kappav[k].alloc(N));
+    CU(c->pid[k].alloc(N)); CU(c->pstate[k].alloc(N));
+  }
+  CU(c->acc.alloc(N)); CU(c->sgp.alloc(N)); CU(c->normal.alloc(N)); CU(c->density.alloc(N)); CU(c->factor.alloc(N));
+  CU(c->dadv.alloc(N)); CU(c->stiff.alloc(N)); CU(c->partials.alloc(N / 128 + 2));
+  CU(c->pos_init.alloc(N)); CU(c->vel_init.alloc(N)); CU(c->kappa_init.alloc(N)); CU(c->kappav_init.alloc(N));
+  const size_t NB = (size_t)std::max(c->n_b, 1);
+  CU(c->bpos.alloc(NB)); CU(c->bvel.alloc(NB)); CU(c->bx0.alloc(NB)); CU(c->bbody.alloc(NB)); CU(c->borig.alloc(NB));
+  CU(c->bvol.alloc(NB));
+  CU(c->dBodies.alloc(std::max<size_t>(c->bodies.size(), 1)));
+  CU(c->dMgr.alloc(std::max<size_t>(c->bodies.size() * c->bodies.size(), 1)));
+  CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
+  const size_t max_scan = std::max<size_t>((size_t)nc + 1, std::max<size_t>(N / 32 + 2, (size_t)c->n_dyn_p + 1));
+  CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
+  CU(c->cell_of_p.alloc(N)); CU(c->rank_in_cell.alloc(N)); CU(c->sorted_src_f.alloc(N));
+  const size_t ND = (size_t)std::max(c->n_dyn_p, 1), NS = (size_t)std::max(c->n_static_p, 1);
+  CU(c->sorted_src_d.alloc(std::max(ND, NS))); CU(c->cell_of_b.alloc(std::max(ND, NS))); CU(c->rank_b.alloc(std::max(ND, NS)));
+  CU(c->cnt_f.alloc(N)); CU(c->cnt_b.alloc(N)); CU(c->woff_f.alloc(N / 32 + 2)); CU(c->woff_b.alloc(N / 32 + 2));
+  const int per_f = cfg.reserved_i[0] > 0 ? cfg.reserved_i[0] : 80;
+  const int per_b = cfg.reserved_i[1] > 0 ? cfg.reserved_i[1] : 48;
+  const int per_d = cfg.reserved_i[2] > 0 ? cfg.reserved_i[2] : 96;
+  const size_t cf = std::min<size_t>((N + 32) * (size_t)per_f, 0xfffffff0u), cb = std::min<size_t>((N + 32) * (size_t)per_b, 0xfffffff0u);
+  c->cap_f = (unsigned int)cf;
+  c->cap_b = (unsigned int)cb;
+  c->cap_d = (unsigned int)(ND * per_d);
+  CU(c->idx_f.alloc(c->cap_f)); CU(c->idx_b.alloc(c->cap_b)); CU(c->idx_d.alloc(c->cap_d)); CU(c->off_d.alloc(ND + 1));
+
+  // ---- accumulator blocks of the boundary-side kernel: one body per block ----
+  std::vector<int> blk_body, blk_first;
+  for (size_t bi = 0; bi < c->bodies.size(); bi++) {
+    HostBody &hb = c->bodies[bi];
+    hb.blk_begin = (int)blk_body.size();
+    hb.blk_count = 0;
+    if (!hb.dynamic) continue;
+    for (int f = 0; f < (int)hb.n; f += BS_PART_PER_BLOCK) {
+      blk_body.push_back((int)bi);
+      blk_first.push_back(hb.p_begin + f);
+      hb.blk_count++;
+    }
+  }
+  c->n_acc_blocks = (int)blk_body.size();
+  CU(c->blk_body.alloc(std::max<size_t>(blk_body.size(), 1)));
+  CU(c->blk_first.alloc(std::max<size_t>(blk_first.size(), 1)));
+  CU(c->acc_rows.alloc(std::max<size_t>(blk_body.size(), 1) * ACC_N));
+  if (!blk_body.empty()) {
+    CU(cudaMemcpy(c->blk_body.p, blk_body.data(), blk_body.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->blk_first.p, blk_first.data(), blk_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+
+  // ---- uploads ----
+  CU(cudaMemcpy(c->dP.p, &P, sizeof(P), cudaMemcpyHostToDevice));
+  if (c->nf0) {
+    std::vector<double4> p4(c->nf0), v4(c->nf0);
+    for (int64_t i = 0; i < c->nf0; i++) {
+      p4[i] = make_double4(c->h_fx[3 * i], c->h_fx[3 * i + 1], c->h_fx[3 * i + 2], 0.0);
+      v4[i] = make_double4(c->h_fv[3 * i], c->h_fv[3 * i + 1], c->h_fv[3 * i + 2], 0.0);
+    }
+    CU(cudaMemcpy(c->pos_init.p, p4.data(), c->nf0 * sizeof(double4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->vel_init.p, v4.data(), c->nf0 * sizeof(double4), cudaMemcpyHostToDevice));
+  }
+  if (c->n_b) {
+    CU(cudaMemcpy(c->bpos.p, h_bpos.data(), c->n_b * sizeof(double4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->bx0.p, h_bx0.data(), c->n_b * sizeof(double4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->bbody.p, h_bbody.data(), c->n_b * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->borig.p, h_borig.data(), c->n_b * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  c->h_borig = h_borig;
+  // ---- one-time physical sort of the static boundary particles into cell order ----
+  if (c->n_static_p > 0) {
+    const int ns = c->n_static_p;
+    CU(c->bpos_tmp.alloc(ns)); CU(c->bx0_tmp.alloc(ns)); CU(c->bbody_tmp.alloc(ns)); CU(c->borig_tmp.alloc(ns));
+    CU(cudaMemsetAsync(c->cell_start_s.p, 0, sizeof(unsigned int) * (nc + 1), c->stream));
+    LAUNCH(c, k_bin_count, cdiv(ns, 128), 128, c->dP.p, c->bpos.p, (const int *)nullptr, ns, c->cell_start_s.p, c->cell_of_b.p,
+           c->rank_b.p);
+    int rc = scan_u32(c, c->cell_start_s.p, (size_t)nc + 1, nullptr);
+    if (rc) return rc;
+    LAUNCH(c, k_bin_scatter, cdiv(ns, 128), 128, (const int *)nullptr, ns, c->cell_start_s.p, c->cell_of_b.p, c->rank_b.p,
+           c->sorted_src_d.p);
+    LAUNCH(c, k_bin_sort_cells, cdiv(nc, 128), 128, c->cell_start_s.p, nc, c->sorted_src_d.p);
+    LAUNCH(c, k_permute_boundary, cdiv(ns, 128), 128, ns, c->sorted_src_d.p, c->bpos.p, c->bx0.p, c->bbody.p, c->borig.p,
+           c->bpos_tmp.p, c->bx0_tmp.p, c->bbody_tmp.p, c->borig_tmp.p);
+    CU(cudaMemcpyAsync(c->bpos.p, c->bpos_tmp.p, ns * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->bx0.p, c->bx0_tmp.p, ns * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->bbody.p, c->bbody_tmp.p, ns * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->borig.p, c->borig_tmp.p, ns * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->h_borig.data(), c->borig.p, ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bpos_tmp.free(); c->bx0_tmp.free(); c->bbody_tmp.free(); c->borig_tmp.free();
+  }
+  c->finalized = true;
+  int rc = reset_device_state(c);
+  if (rc) {
+    c->finalized = false;
+    return rc;
+  }
+  CU(cudaGetLastError());
+  return DFR_OK;
+}
+
+int dfr_load_fluid_state(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  const int64_t n = c->nf0;
+  std::vector<double4> tmp(n);
+  if (x) {
+    for (int64_t i = 0; i < n; i++) tmp[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.0);
+    CU(cudaMemcpy(c->pos_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  }
+  if (v) {
+    for (int64_t i = 0; i < n; i++) tmp[i] = make_double4(v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
+    CU(cudaMemcpy(c->vel_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  }
+  if (kappa) CU(cudaMemcpy(c->kappa_init.p, kappa, n * sizeof(double), cudaMemcpyHostToDevice));
+  if (kappa_v) CU(cudaMemcpy(c->kappav_init.p, kappa_v, n * sizeof(double), cudaMemcpyHostToDevice));
+  // like the oracle, loading re-bases the running state: positions/velocities/kappas are replaced in id order
+  return reset_device_state(c);
+}
+
+int dfr_reset(dfr_context *c) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  return reset_device_state(c);
+}
+
+int dfr_step(dfr_context *c, int n_steps) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (int s = 0; s < n_steps; s++) {
+    int rc = launch_step(c);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  int rc = sync_state(c);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->device_ms += ms;
+  return DFR_OK;
+}
+
+int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  int s = 0;
+  while (s < max_steps) {
+    int rc = launch_step(c);
+    if (rc) return rc;
+    s++;
+    rc = sync_state(c);
+    if (rc) return rc;
+    if (c->hSt->finished) break;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->device_ms += ms;
+  if (steps_done) *steps_done = s;
+  return DFR_OK;
+}
+
+int dfr_get_step_info(dfr_context *c, dfr_step_info *info) {
+  if (!c || !info || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  int rc = sync_state(c);
+  if (rc) return rc;
+  const StepState &s = *c->hSt;
+  info->time = s.time;
+  info->time_step_size = s.h;
+  info->iterations = s.last_iters;
+  info->iterations_v = s.last_iters_v;
+  info->step_count = s.step_count;
+  info->trajectory_finished = s.finished;
+  info->num_fluid_particles = s.nf;
+  info->total_pressure_iterations = s.total_iters;
+  info->total_divergence_iterations = s.total_iters_v;
+  info->total_particle_steps = s.total_particle_steps;
+  info->total_fluid_neighbors = s.total_neighbors;
+  return DFR_OK;
+}
+
+static int fetch_body(dfr_context *c, int body, BodyDev &B) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  if (body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
+  cudaSetDevice(c->device);
+  CU(cudaMemcpyAsync(&B, c->dBodies.p + body, sizeof(BodyDev), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DFR_OK;
+}
+
+int dfr_get_body_state(dfr_context *c, int body, double out[13]) {
+  BodyDev B;
+  int rc = fetch_body(c, body, B);
+  if (rc) return rc;
+  out[0] = B.pos.x; out[1] = B.pos.y; out[2] = B.pos.z;
+  out[3] = B.q.w; out[4] = B.q.x; out[5] = B.q.y; out[6] = B.q.z;
+  out[7] = B.vel.x; out[8] = B.vel.y; out[9] = B.vel.z;
+  out[10] = B.omega.x; out[11] = B.omega.y; out[12] = B.omega.z;
+  return DFR_OK;
+}
+
+int dfr_set_body_velocity(dfr_context *c, int body, const double v[3], const double omega[3]) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  if (body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
+  cudaSetDevice(c->device);
+  BodyDev *d = c->dBodies.p + body;
+  if (v) {
+    const d3 t = mk3(v[0], v[1], v[2]);
+    CU(cudaMemcpyAsync(&d->vel, &t, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (omega) {
+    const d3 t = mk3(omega[0], omega[1], omega[2]);
+    CU(cudaMemcpyAsync(&d->omega, &t, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return DFR_OK;
+}
+
+int dfr_get_body_properties(dfr_context *c, int body, double out[17]) {
+  BodyDev B;
+  int rc = fetch_body(c, body, B);
+  if (rc) return rc;
+  out[0] = B.mass;
+  out[1] = B.inv_mass;
+  for (int k = 0; k < 9; k++) out[2 + k] = B.I0.a[k];
+  out[11] = B.force_last.x; out[12] = B.force_last.y; out[13] = B.force_last.z;
+  out[14] = B.torque_last.x; out[15] = B.torque_last.y; out[16] = B.torque_last.z;
+  return DFR_OK;
+}
+
+int dfr_get_body_grad(dfr_context *c, int body, int which, double out[12]) {
+  BodyDev B;
+  int rc = fetch_body(c, body, B);
+  if (rc) return rc;
+  std::memset(out, 0, 12 * sizeof(double));
+  switch (which) {
+    case 0: put(out, B.x_v0); break;
+    case 1: put(out, B.x_w0); break;
+    case 2: put(out, B.q_v0); break;
+    case 3: put(out, B.q_w0); break;
+    case 4: put(out, B.v_v0); break;
+    case 5: put(out, B.v_w0); break;
+    case 6: put(out, B.w_v0); break;
+    case 7: put(out, B.w_w0); break;
+    case 8: put(out, B.net_f_v); break;
+    case 9: put(out, B.net_f_x); break;
+    case 10: put(out, B.net_f_q); break;
+    case 11: put(out, B.net_f_w); break;
+    case 12: put(out, B.net_t_v); break;
+    case 13: put(out, B.net_t_x); break;
+    case 14: put(out, B.net_t_q); break;
+    case 15: put(out, B.net_t_w); break;
+    default: return fail(c, DFR_ERR_INVALID, "bad gradient selector");
+  }
+  return DFR_OK;
+}
+
+int dfr_get_manager_grad(dfr_context *c, int R, int RR, int which, double out[12]) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  const int n = (int)c->bodies.size();
+  if (R < 0 || RR < 0 || R >= n || RR >= n) return fail(c, DFR_ERR_INVALID, "bad body index");
+  cudaSetDevice(c->device);
+  MgrBlock M;
+  CU(cudaMemcpyAsync(&M, c->dMgr.p + (R * n + RR), sizeof(MgrBlock), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memset(out, 0, 12 * sizeof(double));
+  switch (which) {
+    case 0: put(out, M.xn_v0); break;
+    case 1: put(out, M.xn_w0); break;
+    case 2: put(out, M.qn_v0); break;
+    case 3: put(out, M.qn_w0); break;
+    case 4: put(out, M.vn_v0); break;
+    case 5: put(out, M.vn_w0); break;
+    case 6: put(out, M.wn_v0); break;
+    case 7: put(out, M.wn_w0); break;
+    case 8: put(out, M.f_vn); break;
+    case 9: put(out, M.f_xn); break;
+    case 10: put(out, M.f_qn); break;
+    case 11: put(out, M.f_wn); break;
+    case 12: put(out, M.t_vn); break;
+    case 13: put(out, M.t_xn); break;
+    case 14: put(out, M.t_qn); break;
+    case 15: put(out, M.t_wn); break;
+    default: return fail(c, DFR_ERR_INVALID, "bad gradient selector");
+  }
+  return DFR_OK;
+}
+
+int64_t dfr_num_fluid(dfr_context *c) {
+  if (!c || !c->finalized) return c ? c->nf0 : 0;
+  cudaSetDevice(c->device);
+  if (sync_state(c)) return 0;
+  return c->hSt->nf;
+}
+int64_t dfr_num_body_particles(dfr_context *c, int body) {
+  return (c && body >= 0 && body < (int)c->bodies.size()) ? c->bodies[body].n : 0;
+}
+int dfr_num_bodies(dfr_context *c) { return c ? (int)c->bodies.size() : 0; }
+
+int dfr_download_fluid(dfr_context *c, int field, double *out) {
+  if (!c || !c->finalized || !out) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  int rc = sync_state(c);
+  if (rc) return rc;
+  const int n = c->hSt->nf;
+  if (n == 0) return DFR_OK;
+  std::vector<int> ids(n);
+  CU(cudaMemcpy(ids.data(), c->pid[c->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  const double4 *v4 = nullptr;
+  const double *s1 = nullptr;
+  switch (field) {
+    case 0: v4 = c->pos[c->cur].p; break;
+    case 1: v4 = c->vel[c->vcur].p; break;
+    case 2: s1 = c->density.p; break;
+    case 3: s1 = c->factor.p; break;
+    case 4: s1 = c->kappa[c->cur].p; break;
+    case 5: s1 = c->kappav[c->cur].p; break;
+    case 6: s1 = c->dadv.p; break;
+    case 7: v4 = c->acc.p; break;
+    case 8: v4 = c->sgp.p; break;
+    case 9: v4 = c->normal.p; break;
+    default: return fail(c, DFR_ERR_INVALID, "bad field");
+  }
+  if (v4) {
+    std::vector<double4> t(n);
+    CU(cudaMemcpy(t.data(), v4, n * sizeof(double4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+      double *o = out + 3 * (size_t)ids[i];
+      o[0] = t[i].x; o[1] = t[i].y; o[2] = t[i].z;
+    }
+  } else {
+    std::vector<double> t(n);
+    CU(cudaMemcpy(t.data(), s1, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) out[ids[i]] = t[i];
+  }
+  return DFR_OK;
+}
+
+int dfr_download_body(dfr_context *c, int body, int field, double *out) {
+  if (!c || !c->finalized || !out) return fail(c, DFR_ERR_STATE, "not finalized");
+  if (body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
+  cudaSetDevice(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  const HostBody &hb = c->bodies[body];
+  const double4 *src = nullptr;
+  switch (field) {
+    case 0: case 2: src = c->bpos.p; break;
+    case 1: src = c->bvel.p; break;
+    case 3: src = c->bx0.p; break;
+    default: return fail(c, DFR_ERR_INVALID, "bad field");
+  }
+  if (hb.dynamic) {
+    std::vector<double4> t(hb.n);
+    CU(cudaMemcpy(t.data(), src + hb.p_begin, hb.n * sizeof(double4), cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < hb.n; j++) {
+      if (field == 2)
+        out[j] = t[j].w;
+      else {
+        out[3 * j] = t[j].x; out[3 * j + 1] = t[j].y; out[3 * j + 2] = t[j].z;
+      }
+    }
+  } else {
+    std::vector<double4> t(c->n_static_p);
+    CU(cudaMemcpy(t.data(), src, c->n_static_p * sizeof(double4), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < c->n_static_p; s++) {
+      const int g = c->h_borig[s];
+      if (g < hb.p_begin || g >= hb.p_begin + hb.n) continue;
+      const int64_t j = g - hb.p_begin;
+      if (field == 2)
+        out[j] = t[s].w;
+      else {
+        out[3 * j] = t[s].x; out[3 * j + 1] = t[s].y; out[3 * j + 2] = t[s].z;
+      }
+    }
+  }
+  return DFR_OK;
+}
+
+int dfr_get_neighbors(dfr_context *c, int set_a, int set_b, int32_t *counts, int32_t *indices, int64_t capacity, int64_t *total) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  const int nb = (int)c->bodies.size();
+  if (set_a < -1 || set_a >= nb || set_b < -1 || set_b >= nb) return fail(c, DFR_ERR_INVALID, "bad set index");
+  cudaSetDevice(c->device);
+  // the same neighbourhood build the step runs, on the current positions
+  int rc = build_neighbors(c);
+  if (rc) return rc;
+  rc = sync_state(c);
+  if (rc) return rc;
+  const int n = c->hSt->nf;
+  std::vector<int> ids(std::max(n, 1));
+  if (n) CU(cudaMemcpy(ids.data(), c->pid[c->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<std::vector<int32_t>> rows;
+  if (set_a == -1) {
+    const bool fluid = (set_b == -1);
+    rows.assign(n, {});
+    if (n) {
+      const int nw = (n + 31) / 32;
+      std::vector<int> cnt(n);
+      std::vector<unsigned int> woff(nw + 1);
+      CU(cudaMemcpy(cnt.data(), fluid ? c->cnt_f.p : c->cnt_b.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(woff.data(), fluid ? c->woff_f.p : c->woff_b.p, (nw + 1) * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+      std::vector<int> idx(std::max<size_t>(woff[nw], 1));
+      if (woff[nw]) CU(cudaMemcpy(idx.data(), fluid ? c->idx_f.p : c->idx_b.p, (size_t)woff[nw] * sizeof(int), cudaMemcpyDeviceToHost));
+      const HostBody *hb = fluid ? nullptr : &c->bodies[set_b];
+      for (int i = 0; i < n; i++) {
+        std::vector<int32_t> &r = rows[ids[i]];
+        for (int k = 0; k < cnt[i]; k++) {
+          const int j = idx[(size_t)woff[i >> 5] + (size_t)k * 32 + (i & 31)];
+          if (fluid)
+            r.push_back(ids[j]);
+          else {
+            const int g = c->h_borig[j];
+            if (g >= hb->p_begin && g < hb->p_begin + hb->n) r.push_back(g - hb->p_begin);
+          }
+        }
+        std::sort(r.begin(), r.end());
+      }
+    }
+  } else if (set_b == -1 && c->bodies[set_a].dynamic) {
+    const HostBody &hb = c->bodies[set_a];
+    rows.assign(hb.n, {});
+    std::vector<unsigned int> off(c->n_dyn_p + 1);
+    CU(cudaMemcpy(off.data(), c->off_d.p, (c->n_dyn_p + 1) * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    std::vector<int> idx(std::max<size_t>(off[c->n_dyn_p], 1));
+    if (off[c->n_dyn_p]) CU(cudaMemcpy(idx.data(), c->idx_d.p, (size_t)off[c->n_dyn_p] * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < hb.n; j++) {
+      const int t = hb.p_begin - c->dyn_begin + (int)j;
+      for (unsigned int p = off[t]; p < off[t + 1]; p++) rows[j].push_back(ids[idx[p]]);
+      std::sort(rows[j].begin(), rows[j].end());
+    }
+  } else
+    return fail(c, DFR_ERR_INVALID, "only fluid->fluid, fluid->body and dynamic body->fluid neighbour sets are stored (Simulation.cpp:882-900)");
+  int64_t tot = 0;
+  for (size_t i = 0; i < rows.size(); i++) {
+    if (counts) counts[i] = (int32_t)rows[i].size();
+    if (indices) {
+      if (tot + (int64_t)rows[i].size() > capacity) return fail(c, DFR_ERR_CAPACITY, "neighbour buffer too small");
+      std::memcpy(indices + tot, rows[i].data(), rows[i].size() * sizeof(int32_t));
+    }
+    tot += (int64_t)rows[i].size();
+  }
+  if (total) *total = tot;
+  return DFR_OK;
+}
+
+int dfr_get_device_time_ms(dfr_context *c, double *total_ms, int64_t *kernel_launches) {
+  if (!c) return DFR_ERR_INVALID;
+  if (total_ms) *total_ms = c->device_ms;
+  if (kernel_launches) *kernel_launches = c->launches;
+  return DFR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1102 @@
+// Hand-written sm_100a kernels of the differentiable DFSPH time step.
+// Each kernel cites the reference loop it replaces (paths relative to the reference checkout).
+// Layout rules: fluid particles are re-sorted into cell order every step, positions
+// and velocities are 32-byte double4 records (one sector per gathered neighbour), neighbour
+// lists are warp-interleaved so index loads coalesce, no tensor cores (no dense contraction).
+#pragma once
+#include "dfr_types.cuh"
+
+namespace dfr {
+
+#define DFR_EPS 1.0e-5  // m_eps, TimeStepDiffDFSPH.h:26
+#define DFR_FULL 0xffffffffu
+
+// read-only 32-byte record load (two 128-bit LDG.NC on the same sector)
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell coordinates
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ void cell_of(const GridGeom &g, double x, double y, double z, int &cx, int &cy, int &cz) {
+  cx = clampi((int)floor((x - g.ox) * g.inv_cell), 0, g.nx - 1);
+  cy = clampi((int)floor((y - g.oy) * g.inv_cell), 0, g.ny - 1);
+  cz = clampi((int)floor((z - g.oz) * g.inv_cell), 0, g.nz - 1);
+}
+__device__ __forceinline__ int cell_lin(const GridGeom &g, int cx, int cy, int cz) { return (cz * g.ny + cy) * g.nx + cx; }
+
+// CompactNSearch distance predicate (upstream @3f11ece1): l2 = dx*dx; l2 += dy*dy; l2 += dz*dz;
+// l2 < r2.  Written with explicit round-to-nearest intrinsics so that nvcc cannot contract it into
+// FMAs: neighbour sets then match the oracle (built with -ffp-contract=off) bit for bit.
+__device__ __forceinline__ double dist2_exact(double ax, double ay, double az, double bx, double by, double bz) {
+  double t = __dsub_rn(ax, bx);
+  double l2 = __dmul_rn(t, t);
+  t = __dsub_rn(ay, by);
+  l2 = __dadd_rn(l2, __dmul_rn(t, t));
+  t = __dsub_rn(az, bz);
+  l2 = __dadd_rn(l2, __dmul_rn(t, t));
+  return l2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPH kernel functions (SPHKernels.h:37-55, 80-102, 123-150, 483-499, 544-556)
+// ---------------------------------------------------------------------------------------------
+// Returns W(|r|) and writes c with gradW(r) = c * r.
+__device__ __forceinline__ double cubic_W_and_grad(const Params &P, double r2, double &c) {
+  double rl, rinv;
+  if (r2 > 1.0e-10) {  // rl > 1e-5
+    rinv = rsqrt(r2);
+    rl = r2 * rinv;
+  } else {
+    rl = sqrt(r2);
+    rinv = 0.0;
+  }
+  const double q = rl * P.inv_h;
+  double w;
+  if (q <= 0.5) {
+    const double q2 = q * q;
+    w = P.k_cubic * (6.0 * q2 * q - 6.0 * q2 + 1.0);
+    c = P.l_cubic * q * (3.0 * q - 2.0);
+  } else {
+    const double f = fmax(1.0 - q, 0.0);
+    w = P.k_cubic * 2.0 * f * f * f;
+    c = -P.l_cubic * f * f;
+  }
+  c *= rinv * P.inv_h;
+  return w;
+}
+__device__ __forceinline__ double cubic_grad_coeff(const Params &P, double r2) {
+  if (!(r2 > 1.0e-10)) return 0.0;
+  const double rinv = rsqrt(r2);
+  const double q = r2 * rinv * P.inv_h;
+  double c;
+  if (q <= 0.5)
+    c = P.l_cubic * q * (3.0 * q - 2.0);
+  else {
+    const double f = fmax(1.0 - q, 0.0);
+    c = -P.l_cubic * f * f;
+  }
+  return c * rinv * P.inv_h;
+}
+__device__ __forceinline__ d3 cubic_gradW(const Params &P, d3 r) { return cubic_grad_coeff(P, dot(r, r)) * r; }
+__device__ __forceinline__ double cubic_W(const Params &P, double r2) {
+  const double q = sqrt(r2) * P.inv_h;
+  if (q > 1.0) return 0.0;
+  if (q <= 0.5) {
+    const double q2 = q * q;
+    return P.k_cubic * (6.0 * q2 * q - 6.0 * q2 + 1.0);
+  }
+  const double f = 1.0 - q;
+  return P.k_cubic * 2.0 * f * f * f;
+}
+// gradW and gradGradW of r (CubicKernel::gradGradW, SPHKernels.h:123-150)
+__device__ __forceinline__ void cubic_grad_gradgrad(const Params &P, d3 r, d3 &g, m33 &H) {
+  const double r2 = dot(r, r);
+  if (!(r2 > 1.0e-10)) {
+    g = mk3(0, 0, 0);
+    H = m33::zero();
+    return;
+  }
+  const double rl = sqrt(r2);
+  const double q = rl * P.inv_h;
+  if (q > 1.0) {
+    g = mk3(0, 0, 0);
+    H = m33::zero();
+    return;
+  }
+  const double s = 1.0 / (rl * P.support_radius);
+  const d3 gradq = s * r;
+  double c1, c2;
+  if (q <= 0.5) {
+    c1 = P.l_cubic * q * (3.0 * q - 2.0);
+    c2 = P.l_cubic * (6.0 * q - 2.0);
+  } else {
+    const double f = 1.0 - q;
+    c1 = P.l_cubic * (-f * f);
+    c2 = P.l_cubic * 2.0 * f;
+  }
+  g = c1 * gradq;
+  const m33 rr = outer(r, r);
+  const m33 gg = outer(gradq, gradq);
+  const double ir2 = 1.0 / r2;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) H.a[i * 3 + j] = c1 * s * ((i == j ? 1.0 : 0.0) - rr.a[i * 3 + j] * ir2) + c2 * gg.a[i * 3 + j];
+}
+__device__ __forceinline__ double cube(double x) { return x * x * x; }
+__device__ __forceinline__ double cohesion_W(const Params &P, double r2) {
+  const double h = P.support_radius;
+  if (!(r2 <= h * h)) return 0.0;
+  const double r1 = sqrt(r2);
+  const double r3 = r2 * r1;
+  if (r1 > 0.5 * h) return P.coh_k * cube(h - r1) * r3;
+  return P.coh_k * 2.0 * cube(h - r1) * r3 - P.coh_c;
+}
+__device__ __forceinline__ double adhesion_W(const Params &P, double r2) {
+  const double h = P.support_radius;
+  if (!(r2 <= h * h)) return 0.0;
+  const double rl = sqrt(r2);
+  if (rl > 0.5 * h) return P.adh_k * pow(-4.0 * r2 / h + 6.0 * rl - 2.0 * h, 0.25);
+  return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill_i32(int *p, int v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// exclusive scan of unsigned ints, 3 kernels (block scan, scan of block sums, add offsets)
+#define SCAN_THREADS 512
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+__global__ void k_scan_tiles(const unsigned int *in, unsigned int *out, unsigned int *tile_sums, size_t n) {
+  __shared__ unsigned int warp_sums[SCAN_THREADS / 32];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  unsigned int v[SCAN_ITEMS];
+  unsigned int sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    sum += v[k];
+  }
+  // inclusive scan of thread sums
+  unsigned int incl = sum;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(DFR_FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned int ws = (lane < SCAN_THREADS / 32) ? warp_sums[lane] : 0u;
+    unsigned int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(DFR_FULL, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - ws;  // exclusive
+    if (lane == SCAN_THREADS / 32 - 1) tile_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  unsigned int run = warp_sums[wid] + (incl - sum);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+}
+// single block: exclusive scan of the tile sums in place; writes the grand total to *total
+__global__ void k_scan_sums(unsigned int *tile_sums, int ntiles, unsigned int *total) {
+  __shared__ unsigned int warp_sums[32];
+  __shared__ unsigned int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < ntiles; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const unsigned int v = (i < ntiles) ? tile_sums[i] : 0u;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(DFR_FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned int ws = warp_sums[lane];
+      unsigned int wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(DFR_FULL, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    const unsigned int carry = carry_s;
+    const unsigned int excl = carry + warp_sums[wid] + (incl - v);
+    if (i < ntiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry_s;
+}
+__global__ void k_scan_add(unsigned int *out, const unsigned int *tile_sums, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell binning / counting sort (replaces CompactNSearch's hash-grid build; call site
+// Simulation.cpp:746 find_neighbors, and z_sort Simulation.cpp:755)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bin_count(const Params *Pp, const double4 *pos, const int *n_ptr, int n_fixed, unsigned int *cell_count,
+                            int *cell_of_particle, int *rank_in_cell) {
+  const Params &P = *Pp;
+  const int n = n_ptr ? *n_ptr : n_fixed;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = pos[i];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int c = cell_lin(P.grid, cx, cy, cz);
+  cell_of_particle[i] = c;
+  rank_in_cell[i] = (int)atomicAdd(&cell_count[c], 1u);
+}
+// slot[cell_start + rank] = i, then each cell's slice is sorted by i so the permutation is the
+// (deterministic) stable counting sort irrespective of the order the atomics were served in.
+__global__ void k_bin_scatter(const int *n_ptr, int n_fixed, const unsigned int *cell_start, const int *cell_of_particle,
+                              const int *rank_in_cell, int *sorted_src) {
+  const int n = n_ptr ? *n_ptr : n_fixed;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sorted_src[cell_start[cell_of_particle[i]] + rank_in_cell[i]] = i;
+}
+__global__ void k_bin_sort_cells(const unsigned int *cell_start, int ncells, int *sorted_src) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int s = (int)cell_start[c], e = (int)cell_start[c + 1];
+  const int m = e - s;
+  if (m < 2) return;
+  int *a = sorted_src + s;
+  if (m <= 64) {  // insertion sort
+    for (int i = 1; i < m; i++) {
+      const int v = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > v) {
+        a[j + 1] = a[j];
+        j--;
+      }
+      a[j + 1] = v;
+    }
+  } else {  // heap sort (edge cells collecting escaped particles)
+    for (int start = m / 2 - 1; start >= 0; start--) {
+      int root = start;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= m) break;
+        if (child + 1 < m && a[child] < a[child + 1]) child++;
+        if (a[root] >= a[child]) break;
+        const int t = a[root]; a[root] = a[child]; a[child] = t;
+        root = child;
+      }
+    }
+    for (int end = m - 1; end > 0; end--) {
+      const int t0 = a[0]; a[0] = a[end]; a[end] = t0;
+      int root = 0;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= end) break;
+        if (child + 1 < end && a[child] < a[child + 1]) child++;
+        if (a[root] >= a[child]) break;
+        const int t = a[root]; a[root] = a[child]; a[child] = t;
+        root = child;
+      }
+    }
+  }
+}
+// gather every persistent per-particle array into cell order (replaces FluidModel::
+// performNeighborhoodSearchSort + SimulationDataDiffDFSPH::performNeighborhoodSearchSort,
+// FluidModel.cpp:357-386, SimulationDataDiffDFSPH.cpp:150-171 — done every step here)
+__global__ void k_permute_fluid(const StepState *st, const int *sorted_src, const double4 *pos_in, const double4 *vel_in,
+                                const double *kappa_in, const double *kappav_in, const int *id_in, const int *state_in,
+                                double4 *pos_out, double4 *vel_out, double *kappa_out, double *kappav_out, int *id_out,
+                                int *state_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  const int s = sorted_src[i];
+  pos_out[i] = pos_in[s];
+  vel_out[i] = vel_in[s];
+  kappa_out[i] = kappa_in[s];
+  kappav_out[i] = kappav_in[s];
+  id_out[i] = id_in[s];
+  state_out[i] = state_in[s];
+}
+// one-time physical sort of the static boundary particles
+__global__ void k_permute_boundary(int n, const int *sorted_src, const double4 *pos_in, const double4 *x0_in, const int *body_in,
+                                   const int *orig_in, double4 *pos_out, double4 *x0_out, int *body_out, int *orig_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = sorted_src[i];
+  pos_out[i] = pos_in[s];
+  x0_out[i] = x0_in[s];
+  body_out[i] = body_in[s];
+  orig_out[i] = orig_in[s];
+}
+
+// ---------------------------------------------------------------------------------------------
+// neighbour lists
+// ---------------------------------------------------------------------------------------------
+struct GridView {
+  const unsigned int *cell_start;  // ncells + 1
+  const int *sorted_src;           // nullptr: points are physically in cell order; else slot -> point (relative)
+  const double4 *pos;              // points of this set
+  int base;                        // added to the point index stored in the list
+};
+
+// Visits every point of `g` within the support radius of (px,py,pz); f(index) with index = base + point.
+template <class F>
+__device__ __forceinline__ void for_each_in_range(const Params &P, const GridView &g, double px, double py, double pz, int self, F f) {
+  int cx, cy, cz;
+  cell_of(P.grid, px, py, pz, cx, cy, cz);
+  const int xlo = max(cx - 1, 0), xhi = min(cx + 1, P.grid.nx - 1);
+  for (int z = max(cz - 1, 0); z <= min(cz + 1, P.grid.nz - 1); z++)
+    for (int y = max(cy - 1, 0); y <= min(cy + 1, P.grid.ny - 1); y++) {
+      const int s = (int)g.cell_start[cell_lin(P.grid, xlo, y, z)];
+      const int e = (int)g.cell_start[cell_lin(P.grid, xhi, y, z) + 1];
+      for (int p = s; p < e; p++) {
+        const int j = g.sorted_src ? g.sorted_src[p] : p;
+        if (j == self) continue;
+        const double4 q = ldg4(g.pos + j);
+        if (dist2_exact(px, py, pz, q.x, q.y, q.z) < P.r2) f(g.base + j);
+      }
+    }
+}
+
+// pass 1: counts (fluid->fluid, fluid->boundary) and the per-warp slice size 32 * max(count)
+__global__ void __launch_bounds__(128) k_nbr_count(const Params *Pp, const StepState *st, const double4 *pos, GridView gf, GridView gs,
+                                                    GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
+                                                    unsigned int *wsize_f, unsigned int *wsize_b) {
+  const Params &P = *Pp;
+  const int n = st->nf;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cf = 0, cb = 0;
+  if (i < n) {
+    const double4 p = pos[i];
+    for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int) { cf++; });
+    if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int) { cb++; });
+    if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int) { cb++; });
+    cnt_f[i] = cf;
+    cnt_b[i] = cb;
+  }
+  const int mf = __reduce_max_sync(DFR_FULL, cf);
+  const int mb = __reduce_max_sync(DFR_FULL, cb);
+  if ((threadIdx.x & 31) == 0 && (i < n)) {
+    wsize_f[i >> 5] = 32u * (unsigned int)mf;
+    wsize_b[i >> 5] = 32u * (unsigned int)mb;
+  }
+}
+// pass 2: fill the warp-interleaved lists
+__global__ void __launch_bounds__(128) k_nbr_fill(const Params *Pp, StepState *st, const double4 *pos, GridView gf, GridView gs, GridView gd,
+                                                   int has_static, int has_dyn, const unsigned int *woff_f, const unsigned int *woff_b,
+                                                   int *idx_f, int *idx_b, unsigned int cap_f, unsigned int cap_b) {
+  const Params &P = *Pp;
+  const int n = st->nf;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int lane = i & 31, w = i >> 5;
+  const int nw = (n + 31) >> 5;
+  const double4 p = pos[i];
+  // woff has nw + 1 entries (exclusive scan incl. total)
+  const bool ok_f = woff_f[w + 1] <= cap_f;
+  const bool ok_b = woff_b[w + 1] <= cap_b;
+  if (!ok_f) atomicOr(&st->error_flags, 1);
+  if (!ok_b) atomicOr(&st->error_flags, 2);
+  if (i == 0) {
+    st->list_used_f = woff_f[nw];
+    st->list_used_b = woff_b[nw];
+  }
+  if (ok_f) {
+    int *o = idx_f + woff_f[w] + lane;
+    int k = 0;
+    for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int j) {
+      o[(size_t)k * 32] = j;
+      k++;
+    });
+  }
+  if (ok_b) {
+    int *o = idx_b + woff_b[w] + lane;
+    int k = 0;
+    if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int j) {
+      o[(size_t)k * 32] = j;
+      k++;
+    });
+    if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int j) {
+      o[(size_t)k * 32] = j;
+      k++;
+    });
+  }
+}
+// dynamic boundary particle -> fluid neighbours, CSR rows (one warp later walks one row)
+__global__ void __launch_bounds__(128) k_dnbr_count(const Params *Pp, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf, unsigned int *cnt_d) {
+  const Params &P = *Pp;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_dyn) return;
+  const double4 p = bpos[dyn_begin + t];
+  unsigned int c = 0;
+  for_each_in_range(P, gf, p.x, p.y, p.z, -1, [&](int) { c++; });
+  cnt_d[t] = c;
+}
+__global__ void __launch_bounds__(128) k_dnbr_fill(const Params *Pp, StepState *st, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf,
+                                                    const unsigned int *off_d, int *idx_d, unsigned int cap_d) {
+  const Params &P = *Pp;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_dyn) return;
+  if (off_d[t + 1] > cap_d) {
+    atomicOr(&st->error_flags, 4);
+    return;
+  }
+  if (t == 0) st->list_used_d = off_d[n_dyn];
+  const double4 p = bpos[dyn_begin + t];
+  int *o = idx_d + off_d[t];
+  for_each_in_range(P, gf, p.x, p.y, p.z, -1, [&](int j) { *o++ = j; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary volume psi (Simulation::updateBoundaryVolume, Simulation.cpp:831-902;
+// BoundaryModel_Akinci2012::computeBoundaryVolume, BoundaryModel_Akinci2012.cpp:257-284)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_boundary_volume(const Params *Pp, double4 *bpos, int n_b, int n_static, GridView gs, GridView gd,
+                                                          int has_static, int has_dyn, double *vol_out) {
+  const Params &P = *Pp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_b) return;
+  const double4 p = bpos[b];
+  double delta = P.W_zero;
+  const int self_s = (b < n_static) ? b : -1;
+  const int self_d = (b >= n_static) ? b - n_static : -1;
+  if (has_static)
+    for_each_in_range(P, gs, p.x, p.y, p.z, self_s, [&](int j) {
+      const double4 q = ldg4(bpos + j);
+      const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+      delta += cubic_W(P, dx * dx + dy * dy + dz * dz);
+    });
+  if (has_dyn)
+    for_each_in_range(P, gd, p.x, p.y, p.z, self_d, [&](int j) {
+      const double4 q = ldg4(bpos + j);
+      const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+      delta += cubic_W(P, dx * dx + dy * dy + dz * dz);
+    });
+  vol_out[b] = 1.0 / delta;
+}
+__global__ void k_store_volume(double4 *bpos, const double *vol, int n_b) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_b) bpos[b].w = vol[b];
+}
+
+// ---------------------------------------------------------------------------------------------
+// density + DFSPH factor, fused (TimeStep::computeDensities, TimeStep.cpp:147-200;
+// computeDFSPHFactor, TimeStepDiffDFSPH.cpp:883-962)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_density_factor(const Params *Pp, const StepState *st, const double4 *pos, const double4 *bpos,
+                                                         NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp) {
+  const Params &P = *Pp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  const double4 pi = pos[i];
+  const int lane = i & 31, w = i >> 5;
+  double dens = P.volume * P.W_zero;
+  double S = 0.0;
+  d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij
+  {
+    const int n = lf.cnt[i];
+    const int *o = lf.idx + lf.woff[w] + lane;
+    for (int k = 0; k < n; k++) {
+      const int j = o[(size_t)k * 32];
+      const double4 pj = ldg4(pos + j);
+      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      double c;
+      const double wv = cubic_W_and_grad(P, dot(r, r), c);
+      dens += P.volume * wv;
+      const d3 g = (P.volume * c) * r;
+      S += dot(g, g);
+      G += g;
+    }
+  }
+  {
+    const int n = lb.cnt[i];
+    const int *o = lb.idx + lb.woff[w] + lane;
+    for (int k = 0; k < n; k++) {
+      const int j = o[(size_t)k * 32];
+      const double4 pj = ldg4(bpos + j);
+      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      double c;
+      const double wv = cubic_W_and_grad(P, dot(r, r), c);
+      dens += pj.w * wv;
+      G += (pj.w * c) * r;
+    }
+  }
+  density[i] = dens * P.density0;
+  const double denom = S + dot(G, G);
+  factor[i] = (denom > DFR_EPS) ? -1.0 / denom : 0.0;
+  sgp[i] = make_double4(-G.x, -G.y, -G.z, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// velocity-divergence pass: computeDensityChange / computeDensityAdv (+ warm-start clamps, the
+// stiffness for the next push, and the residual reduction with on-device convergence control)
+// TimeStepDiffDFSPH.cpp:1926-2041, 964-999, 1698-1732, 1203-1216, 1906-1915, 711-743, 828-861
+// ---------------------------------------------------------------------------------------------
+enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
+
+template <bool PRESSURE, int MODE>
+__global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+                                              const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
+                                              const int *state, double *kappa, double *dadv, double *stiff, double *partials) {
+  const Params &P = *Pp;
+  if (MODE == RHO_ITER) {
+    if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+  }
+  const int nf = st->nf;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double h = PRESSURE ? st->h : st->h_step;
+  double err = 0.0;
+  if (i < nf) {
+    const double4 pi = pos[i];
+    const double4 vi = vel[i];
+    const int lane = i & 31, w = i >> 5;
+    double delta = 0.0;
+    const int nF = lf.cnt[i];
+    {
+      const int *o = lf.idx + lf.woff[w] + lane;
+      for (int k = 0; k < nF; k++) {
+        const int j = o[(size_t)k * 32];
+        const double4 pj = ldg4(pos + j);
+        const double4 vj = ldg4(vel + j);
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double c = cubic_grad_coeff(P, dot(r, r));
+        delta += (P.volume * c) * ((vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z);
+      }
+    }
+    const int nB = lb.cnt[i];
+    {
+      const int *o = lb.idx + lb.woff[w] + lane;
+      for (int k = 0; k < nB; k++) {
+        const int j = o[(size_t)k * 32];
+        const double4 pj = ldg4(bpos + j);
+        const double4 vj = ldg4(bvel + j);
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double c = cubic_grad_coeff(P, dot(r, r));
+        delta += (pj.w * c) * ((vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z);
+      }
+    }
+    double rho;
+    if (PRESSURE) {
+      rho = fmax(density[i] / P.density0 + h * delta, 1.0);
+      err = P.density0 * rho - P.density0;
+    } else {
+      rho = fmax(delta, 0.0);
+      if (nF + nB < 20) rho = 0.0;  // particle deficiency (TimeStepDiffDFSPH.cpp:2027-2040)
+      err = P.density0 * rho;
+    }
+    dadv[i] = rho;
+    if (MODE == RHO_WARM) {
+      double kap;
+      if (PRESSURE)
+        kap = (rho > 1.0) ? 0.5 * fmax(kappa[i], -0.00025) / (h * h) : 0.0;
+      else
+        kap = (rho > 0.0) ? 0.5 * fmax(kappa[i], -0.5) / h : 0.0;
+      if (state[i] != 0) kap = 0.0;  // the reference zeroes these in its second loop (:1008-1012 / :1737-1741)
+      kappa[i] = kap;
+      stiff[i] = kap;
+    } else {
+      const double b = PRESSURE ? rho - 1.0 : rho;
+      stiff[i] = PRESSURE ? b * factor[i] / (h * h) : b * factor[i] / h;
+    }
+  }
+  if (MODE == RHO_ITER) {
+    // deterministic residual: block partials in a fixed order, last block closes the iteration
+    __shared__ double wsum[4];
+    __shared__ bool is_last;
+    double s = err;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(DFR_FULL, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+      __threadfence();
+      const unsigned int nblk = (unsigned int)((nf + 127) / 128);
+      const unsigned int t = atomicAdd(&st->ticket, 1u);
+      is_last = (t == nblk - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int nblk = (nf + 127) / 128;
+      double acc = 0.0;
+      for (int b = threadIdx.x; b < nblk; b += 128) acc += ((volatile double *)partials)[b];
+      // fixed-shape tree over the 128 strided sums
+      __shared__ double red[128];
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        const double avg = red[0] / (double)nf;
+        st->last_residual = avg;
+        st->ticket = 0;
+        if (PRESSURE) {
+          const double eta = P.max_error * 0.01 * P.density0;
+          const int it = st->prs_iters + 1;
+          st->prs_iters = it;
+          const bool chk = (avg <= eta);
+          if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
+        } else {
+          const double eta = (1.0 / h) * P.max_error_v * 0.01 * P.density0;
+          const int it = st->div_iters + 1;
+          st->div_iters = it;
+          const bool chk = (avg <= eta);
+          if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// velocity push (warm starts and Jacobi iterations): TimeStepDiffDFSPH.cpp:1005-1057, 1102-1197,
+// 1734-1786, 1826-1902.  Boundary reaction forces are gathered from the boundary side
+// (k_boundary_side) instead of being scattered from here.
+// ---------------------------------------------------------------------------------------------
+template <bool PRESSURE, bool ITER>
+__global__ void __launch_bounds__(128) k_push(const Params *Pp, const StepState *st, const double4 *pos, double4 *vel, const double4 *bpos,
+                                               NbrList lf, NbrList lb, const double *stiff, const int *state, double *kappa, int accumulate_kappa) {
+  const Params &P = *Pp;
+  if (ITER) {
+    if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  if (state[i] != 0) return;
+  const double h = PRESSURE ? st->h : st->h_step;
+  const double ki = stiff[i];
+  if (ITER && accumulate_kappa) kappa[i] += ki;
+  const double4 pi = pos[i];
+  double4 v = vel[i];
+  const int lane = i & 31, w = i >> 5;
+  d3 dv = mk3(0, 0, 0);
+  {
+    const int n = lf.cnt[i];
+    const int *o = lf.idx + lf.woff[w] + lane;
+    for (int k = 0; k < n; k++) {
+      const int j = o[(size_t)k * 32];
+      const double kSum = ki + __ldg(stiff + j);
+      if (fabs(kSum) > DFR_EPS) {
+        const double4 pj = ldg4(pos + j);
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double c = cubic_grad_coeff(P, dot(r, r));
+        // vel -= h * kSum * (-V gradW)
+        dv += (h * kSum * P.volume * c) * r;
+      }
+    }
+  }
+  if (fabs(ki) > DFR_EPS) {
+    const int n = lb.cnt[i];
+    const int *o = lb.idx + lb.woff[w] + lane;
+    for (int k = 0; k < n; k++) {
+      const int j = o[(size_t)k * 32];
+      const double4 pj = ldg4(bpos + j);
+      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      const double c = cubic_grad_coeff(P, dot(r, r));
+      dv += (h * ki * pj.w * c) * r;
+    }
+  }
+  v.x += dv.x;
+  v.y += dv.y;
+  v.z += dv.z;
+  vel[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary side: reaction force/torque on dynamic bodies + the per-pair force/torque Jacobians
+// (BoundaryModel::addForce, BoundaryModel.h:46-58; computeRigidBodyGradient / computeGradient,
+// TimeStepDiffDFSPH.cpp:1226-1694).  One warp per dynamic boundary particle walks its fluid
+// neighbours; 24 pair sums are warp-reduced, lane 0 expands them into the eight Jacobian blocks,
+// per-warp rows are combined in a fixed order (deterministic FP64 sums).
+// ---------------------------------------------------------------------------------------------
+#define BS_WARPS 4
+#define BS_PART_PER_BLOCK 32  // boundary particles per block (8 per warp)
+
+template <int MODE /*0 pressure, 1 divergence*/, bool GRAD>
+__global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const Params *Pp, const StepState *st, const BodyDev *bodies, const int *blk_body,
+                                                                  const int *blk_first, const double4 *pos, const double4 *vel,
+                                                                  const double4 *bpos, const double4 *bvel, const double4 *bx0,
+                                                                  int dyn_begin, const unsigned int *off_d, const int *idx_d,
+                                                                  const double *stiff, const double *dadv, const double *factor,
+                                                                  const double4 *sgp, const int *state, int iter_kernel, double *acc_rows) {
+  const Params &P = *Pp;
+  if (iter_kernel) {
+    if (!(MODE == 0 ? st->prs_active : st->div_active)) return;
+  }
+  __shared__ double rows[BS_WARPS][ACC_N];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = lane; k < ACC_N; k += 32) rows[wid][k] = 0.0;
+  __syncwarp();
+  const int body_id = blk_body[blockIdx.x];
+  const BodyDev &B = bodies[body_id];
+  const bool do_grad = GRAD && !B.animated;
+  const double dt = (MODE == 0) ? st->h : st->h_step;  // re-read from the TimeManager at :1230/:1292
+  const int first = blk_first[blockIdx.x];
+  const int last = min(first + BS_PART_PER_BLOCK, B.p_begin + B.p_count);
+  for (int bj = first + wid; bj < last; bj += BS_WARPS) {
+    const double4 pj = bpos[bj];
+    const double Vj = pj.w;
+    const int t = bj - dyn_begin;
+    const int s = (int)off_d[t], e = (int)off_d[t + 1];
+    double sA[9], sB[9];
+    d3 sFhat = mk3(0, 0, 0), sF = mk3(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 9; k++) sA[k] = sB[k] = 0.0;
+    d3 vj = mk3(0, 0, 0);
+    if (do_grad) {
+      const double4 vv = bvel[bj];
+      vj = mk3(vv.x, vv.y, vv.z);
+    }
+    for (int p = s + lane; p < e; p += 32) {
+      const int i = idx_d[p];
+      const double4 pi = ldg4(pos + i);
+      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      // real reaction force of the push that follows: F = -m dv / dt = m k_i g, g = -V_j gradW
+      const double ki_real = __ldg(stiff + i);
+      if (!do_grad) {
+        if (__ldg(state + i) == 0 && fabs(ki_real) > DFR_EPS) {
+          const double c = cubic_grad_coeff(P, dot(r, r));
+          sF += (-P.mass * ki_real * Vj * c) * r;
+        }
+        continue;
+      }
+      d3 gW;
+      m33 H;
+      cubic_grad_gradgrad(P, r, gW, H);
+      const d3 g = (-Vj) * gW;  // grad_p_j
+      if (__ldg(state + i) == 0 && fabs(ki_real) > DFR_EPS) sF += (P.mass * ki_real) * g;
+      // ---- computeRigidBodyGradient (:1260-1271) ----
+      const double rho = __ldg(dadv + i);
+      const double alpha = __ldg(factor + i);
+      const double b_i = (MODE == 0) ? rho - 1.0 : rho;
+      const double invH = 1.0 / dt, invH2 = 1.0 / dt / dt;
+      const unsigned int coeff_trunc = (unsigned int)((MODE == 0) ? invH2 : invH);  // :1266, truncation reproduced
+      const double ki = b_i * alpha * (double)coeff_trunc;
+      const d3 Fhat = P.mass * ki * g;  // force = -m * (-dt * ki * g) * invH
+      sFhat += Fhat;
+      // ---- computeGradient (:1281-1482) ----
+      const double4 vi4 = ldg4(vel + i);
+      const d3 dvij = mk3(vi4.x - vj.x, vi4.y - vj.y, vi4.z - vj.z);
+      const bool gate = (MODE == 0) ? (rho > 1.0) : (rho > 0.0);
+      const d3 Hdv = H * dvij;
+      d3 grad_b_x = mk3(0, 0, 0), grad_b_v = mk3(0, 0, 0), grad_b_vi = mk3(0, 0, 0);
+      const double4 sg = ldg4(sgp + i);
+      const d3 sumg = mk3(sg.x, sg.y, sg.z);
+      if (gate) {
+        if (MODE == 0) {
+          grad_b_x = (1.0 / P.density0) * g - (dt * Vj) * Hdv;  // :1539-1546 (extra 1/density0 as coded)
+          grad_b_v = (-dt * Vj) * gW;                           // :1600
+          grad_b_vi = (-dt) * sumg;                             // :1632-1663 == dt * sum_j V_j gradW = -dt * sum_grad_p_k
+        } else {
+          grad_b_x = (-Vj) * Hdv;  // :1573
+          grad_b_v = (-Vj) * gW;   // :1624
+          grad_b_vi = -sumg;       // :1665-1694
+        }
+      }
+      d3 grad_alpha_x = mk3(0, 0, 0);
+      if (!(alpha >= 0.0)) grad_alpha_x = (2.0 * alpha * alpha * Vj) * (H * sumg);  // :1485-1516
+      const double coeff = (MODE == 0) ? invH2 : invH;
+      const d3 grad_k_x = coeff * (alpha * grad_b_x + b_i * grad_alpha_x);
+      const d3 grad_k_v = (alpha * coeff) * grad_b_v;
+      const d3 grad_k_vi = (alpha * coeff) * grad_b_vi;
+      // grad_velChange_to_xj = -(g grad_k_x^T + ki * Vj * H)
+      m33 Ax = outer(g, grad_k_x);
+#pragma unroll
+      for (int k = 0; k < 9; k++) Ax.a[k] = -(Ax.a[k] + ki * Vj * H.a[k]);
+      m33 Av = outer(g, grad_k_v);
+      m33 Avi = outer(g, grad_k_vi);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        Av.a[k] = -Av.a[k];
+        Avi.a[k] = -Avi.a[k];
+      }
+      // dF/dx_j = -m Ax ; dF/dv_j = (I - dt Avi)^-1 (-m) Av   (:1396-1397)
+      m33 M = m33::identity();
+#pragma unroll
+      for (int k = 0; k < 9; k++) M.a[k] -= dt * Avi.a[k];
+      const m33 Minv = inverse(M);
+      const m33 dFdv = Minv * ((-P.mass) * Av);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        sA[k] += -P.mass * Ax.a[k];
+        sB[k] += dFdv.a[k];
+      }
+    }
+    // warp reduction of the 24 pair sums (butterfly: every lane ends with the totals)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sF.x += __shfl_xor_sync(DFR_FULL, sF.x, o);
+      sF.y += __shfl_xor_sync(DFR_FULL, sF.y, o);
+      sF.z += __shfl_xor_sync(DFR_FULL, sF.z, o);
+    }
+    if (do_grad) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          sA[k] += __shfl_xor_sync(DFR_FULL, sA[k], o);
+          sB[k] += __shfl_xor_sync(DFR_FULL, sB[k], o);
+        }
+        sFhat.x += __shfl_xor_sync(DFR_FULL, sFhat.x, o);
+        sFhat.y += __shfl_xor_sync(DFR_FULL, sFhat.y, o);
+        sFhat.z += __shfl_xor_sync(DFR_FULL, sFhat.z, o);
+      }
+    }
+    if (lane == 0) {
+      double *row = rows[wid];
+      const d3 xj = mk3(pj.x, pj.y, pj.z);
+      const d3 rj = xj - B.pos;
+      row[ACC_F + 0] += sF.x;
+      row[ACC_F + 1] += sF.y;
+      row[ACC_F + 2] += sF.z;
+      const d3 tq = cross(rj, sF);  // torque += (x_j - x_rb) x f  (BoundaryModel.h:56)
+      row[ACC_T + 0] += tq.x;
+      row[ACC_T + 1] += tq.y;
+      row[ACC_T + 2] += tq.z;
+      if (do_grad) {
+        m33 A, Bm;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          A.a[k] = sA[k];
+          Bm.a[k] = sB[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          row[ACC_FX + k] += A.a[k];
+          row[ACC_FV + k] += Bm.a[k];
+        }
+        if (P.optimize_rotation) {  // :1425-1478
+          const double4 x04 = bx0[bj];
+          const d3 r0 = mk3(x04.x, x04.y, x04.z);
+          const m34 Q = grad_Rqp_to_q(B.q, r0, -1.0);
+          const m33 Sr = skew(rj);
+          const m34 dFdq = A * Q + (Bm * skew(B.omega)) * Q;
+          const m33 dFdw = Bm * transpose(Sr);
+          const m34 dTdq = Sr * dFdq + transpose(skew(sFhat)) * Q;
+          const m33 dTdw = Sr * dFdw;
+          const m33 dTdv = Sr * Bm;
+          const m33 dTdx = Sr * A;
+#pragma unroll
+          for (int k = 0; k < 12; k++) {
+            row[ACC_FQ + k] += dFdq.a[k];
+            row[ACC_TQ + k] += dTdq.a[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            row[ACC_FW + k] += dFdw.a[k];
+            row[ACC_TW + k] += dTdw.a[k];
+            row[ACC_TV + k] += dTdv.a[k];
+            row[ACC_TX + k] += dTdx.a[k];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // combine the warps' rows in a fixed order and add them to this block's global row
+  for (int k = threadIdx.x; k < ACC_N; k += BS_WARPS * 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < BS_WARPS; w2++) s += rows[w2][k];
+    acc_rows[(size_t)blockIdx.x * ACC_N + k] += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// non-pressure forces: SurfaceTension_Akinci2013::computeNormals / step
+// (SurfaceTension_Akinci2013.cpp:25-151), Viscosity_Standard::step (Viscosity_Standard.cpp:233-334),
+// clearAccelerations (TimeStep.cpp:66-81), v += h a (TimeStepDiffDFSPH.cpp:589-604) and the CFL
+// maximum (Simulation.cpp:542-575), fused.  kappa_v *= h_step of divergenceSolve (:870-880) rides along.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_normals(const Params *Pp, const StepState *st, const double4 *pos, NbrList lf, const double *density,
+                                                  double4 *normal) {
+  const Params &P = *Pp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  const double4 pi = pos[i];
+  const int lane = i & 31, w = i >> 5;
+  d3 n = mk3(0, 0, 0);
+  const int cnt = lf.cnt[i];
+  const int *o = lf.idx + lf.woff[w] + lane;
+  for (int k = 0; k < cnt; k++) {
+    const int j = o[(size_t)k * 32];
+    const double4 pj = ldg4(pos + j);
+    const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+    const double c = cubic_grad_coeff(P, dot(r, r));
+    n += (P.mass / __ldg(density + j) * c) * r;
+  }
+  // w carries the particle's density so that the force pass gathers (n_j, rho_j) in one record
+  normal[i] = make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, density[i]);
+}
+
+__global__ void __launch_bounds__(128) k_nonpressure(const Params *Pp, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+                                                      const double4 *bvel, NbrList lf, NbrList lb, const double *density,
+                                                      const double4 *normal, const int *state, double *kappav, int scale_kappav,
+                                                      double4 *acc_out, double4 *vel_out) {
+  const Params &P = *Pp;
+  const int nf = st->nf;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double h = st->h_step;
+  double mag = 0.0;
+  if (i < nf) {
+    const double4 pi = pos[i];
+    const double4 vi = vel[i];
+    const int lane = i & 31, w = i >> 5;
+    d3 a = mk3(P.gx, P.gy, P.gz);
+    const double rhoi = density[i];
+    const bool st_on = (P.st_method == 2);
+    const bool visc_on = (P.visc_method == 1);
+    d3 ni = mk3(0, 0, 0);
+    if (st_on) {
+      const double4 n4 = normal[i];
+      ni = mk3(n4.x, n4.y, n4.z);
+    }
+    const double h2s = P.support_radius * P.support_radius;
+    {
+      const int cnt = lf.cnt[i];
+      const int *o = lf.idx + lf.woff[w] + lane;
+      for (int k = 0; k < cnt; k++) {
+        const int j = o[(size_t)k * 32];
+        const double4 pj = ldg4(pos + j);
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double r2 = dot(r, r);
+        double rhoj;
+        if (st_on) {
+          const double4 nj = ldg4(normal + j);
+          rhoj = nj.w;
+          const double K_ij = 2.0 * P.density0 / (rhoi + rhoj);
+          d3 accel = mk3(0, 0, 0);
+          if (r2 > 1.0e-9) accel -= (P.surface_tension * P.mass * cohesion_W(P, r2) * rsqrt(r2)) * r;
+          accel -= P.surface_tension * mk3(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z);
+          a += K_ij * accel;
+        } else
+          rhoj = __ldg(density + j);
+        if (visc_on) {
+          const double4 vj = ldg4(vel + j);
+          const double c = cubic_grad_coeff(P, r2);
+          const double vx = (vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z;
+          a += (10.0 * P.viscosity * (P.mass / rhoj) * vx / (r2 + 0.01 * h2s) * c) * r;
+        }
+      }
+    }
+    if ((st_on && P.surface_tension_b != 0.0) || (visc_on && P.viscosity_b != 0.0)) {
+      // boundary adhesion / boundary viscosity: zero coefficients in every shipped scene; the
+      // reaction force of the boundary-viscosity term on dynamic bodies is not carried here.
+      const int cnt = lb.cnt[i];
+      const int *o = lb.idx + lb.woff[w] + lane;
+      for (int k = 0; k < cnt; k++) {
+        const int j = o[(size_t)k * 32];
+        const double4 pj = ldg4(bpos + j);
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double r2 = dot(r, r);
+        if (st_on && P.surface_tension_b != 0.0 && r2 > 1.0e-9)
+          a -= (P.surface_tension_b * P.density0 * pj.w * adhesion_W(P, r2) * rsqrt(r2)) * r;
+        if (visc_on && P.viscosity_b != 0.0) {
+          const double4 vj = ldg4(bvel + j);
+          const double c = cubic_grad_coeff(P, r2);
+          const double vx = (vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z;
+          a += (10.0 * P.viscosity_b * (P.density0 * pj.w / rhoi) * vx / (r2 + 0.01 * h2s) * c) * r;
+        }
+      }
+    }
+    acc_out[i] = make_double4(a.x, a.y, a.z, 0.0);
+    const d3 vn = mk3(vi.x + h * a.x, vi.y + h * a.y, vi.z + h * a.z);
+    mag = dot(vn, vn);  // CFL uses (vel + accel*h) with the OLD h for every particle (Simulation.cpp:561-566)
+    if (state[i] == 0)
+      vel_out[i] = make_double4(vn.x, vn.y, vn.z, 0.0);
+    else
+      vel_out[i] = vi;
+    if (scale_kappav) kappav[i] *= h;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mag = fmax(mag, __shfl_xor_sync(DFR_FULL, mag, o));
+  __shared__ double wmax[4];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double m = fmax(fmax(wmax[0], wmax[1]), fmax(wmax[2], wmax[3]));
+    atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// max |v_b|^2 over the particles of dynamic or animated bodies (Simulation.cpp:577-590)
+__global__ void k_cfl_boundary(StepState *st, const double4 *bvel, int dyn_begin, int n_dyn) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double mag = 0.0;
+  if (t < n_dyn) {
+    const double4 v = bvel[dyn_begin + t];
+    mag = v.x * v.x + v.y * v.y + v.z * v.z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mag = fmax(mag, __shfl_xor_sync(DFR_FULL, mag, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(mag));
+}
+
+// Simulation::updateTimeStepSize (Simulation.cpp:524-616) + solver-control reset for the pressure solve
+__global__ void k_cfl_finish(const Params *Pp, StepState *st) {
+  const Params &P = *Pp;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // close the divergence solve bookkeeping
+  st->last_iters_v = st->div_iters;
+  st->total_iters_v += st->div_iters;
+  if (P.cfl_method == 1 || P.cfl_method == 2) {
+    const double maxVel = fmax(0.1, __longlong_as_double((long long)st->cfl_max_bits));
+    const double diameter = 2.0 * P.particle_radius;
+    double h = P.cfl_factor * 0.4 * (diameter / sqrt(maxVel));
+    h = fmin(h, P.cfl_max);
+    h = fmax(h, P.cfl_min);
+    if (P.cfl_method == 2) {
+      double h_old = st->h;
+      if (st->last_iters > 10)
+        h_old *= 0.9;
+      else if (st->last_iters < 5)
+        h_old *= 1.1;
+      h = fmin(h_old, h);
+    }
+    st->h = h;
+  }
+  st->cfl_max_bits = 0ull;
+  st->prs_active = 1;
+  st->prs_iters = 0;
+  st->ticket = 0;
+}
+
+// x += h_step v (TimeStepDiffDFSPH.cpp:615-634), kappa *= h^2 (:752-767)
+__global__ void k_advect_x(const StepState *st, double4 *pos, const double4 *vel, const int *state, double *kappa, int scale_kappa) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  if (state[i] == 0) {
+    const double h = st->h_step;
+    double4 p = pos[i];
+    const double4 v = vel[i];
+    p.x += h * v.x;
+    p.y += h * v.y;
+    p.z += h * v.z;
+    pos[i] = p;
+  }
+  if (scale_kappa) kappa[i] *= st->h * st->h;
+}
+
+__global__ void k_sum_counts(StepState *st, const int *cnt_f, const int *cnt_b) {
+  // neighbour statistics of the step (mean neighbour count feeds the roofline's algorithmic bytes)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  long long c = 0;
+  if (i < st->nf) c = (long long)cnt_f[i] + cnt_b[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(DFR_FULL, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long *)&st->total_neighbors, (unsigned long long)c);
+}
+
+}  // namespace dfr
