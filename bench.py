@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — forward + sensitivity ("adjoint") DiffDFSPH particle-steps/s on B200.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            -> one JSON line, this repository's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  -> one JSON line, the reference's CPU algorithm
+                                                              (oracle/_ref when built, else the oracle port)
+A "step" is one SimulatorBase::timeStepNoGUI body (TimeStepDiffDFSPH::step + sensitivity chain rule + rigid
+update) over the synthetic dam break with 4 dynamic rigid boxes and 2^20 fluid particles (BASELINE.json
+configs[4], the configuration the north-star's throughput target is quoted on).  For N > 1 every rank runs an
+independent rollout of that scene (population sharding, no data-path collective): weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PARTICLES = 1 << 20
+N_BOXES = 4
+CFG = dict(surface_tension_method=2, surface_tension=0.2, target_time=1.0e9, max_error=0.05, max_error_v=0.1)
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_particle_step(nbar, D, P):
+    """SURVEY.md §8d / DESIGN.md: FP64 state streamed once per pass + 4-byte neighbour indices."""
+    return 1212.0 + 48.0 * nbar + D * (176.0 + 8.0 * nbar) + P * (184.0 + 8.0 * nbar)
+
+
+# algorithmic bytes per fluid particle per launch of each kernel; nf/nb = mean fluid /
+# boundary neighbours per particle of the run
+KERNEL_BYTES = {
+    "k_nbr_count": lambda nf, nb: 32 + 8 + 8.0 / 32,
+    "k_nbr_fill": lambda nf, nb: 32 + 8.0 / 32 + 4 * (nf + nb),
+    "k_density_factor": lambda nf, nb: 32 + 8 + 8 + 8 + 32 + 4 * (nf + nb),
+    "k_rho": lambda nf, nb: 32 + 32 + 8 + 8 + 8 + 8 + 8 + 8 + 4 * (nf + nb),
+    "k_push": lambda nf, nb: 32 + 32 + 32 + 8 + 8 + 8 + 4 + 8 + 4 * (nf + nb),
+    "k_normals": lambda nf, nb: 32 + 8 + 8 + 32 + 4 * nf,
+    "k_nonpressure": lambda nf, nb: 32 + 32 + 8 + 32 + 8 + 4 + 16 + 32 + 32 + 4 * nf,
+    "k_permute_fluid": lambda nf, nb: 4 + 2 * (32 + 32 + 8 + 8 + 4 + 4),
+    "k_advect_x": lambda nf, nb: 32 + 32 + 32 + 4 + 16,
+}
+
+
+def kernel_class(name):
+    base = name.strip("()").split("<")[0].strip()
+    return base
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(n_particles):
+    from difffr_b200 import scenes
+
+    return scenes.dam_break_scene(n_particles, n_boxes=N_BOXES)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(lib_path, prefix, scene, steps, warmup):
+    """Time the CPU implementation (oracle port or oracle/_ref) on `scene`; returns (particle-steps/s, cores, ms/step, info)."""
+    from difffr_b200 import scenes
+    from difffr_b200.cabi import Context
+
+    lib = ctypes.CDLL(lib_path)
+    ctx = scenes.build_context(lambda **k: Context(lib=lib, prefix=prefix, **k), scene, **CFG)
+    cores = 1
+    if hasattr(lib, prefix + "num_threads"):
+        f = getattr(lib, prefix + "num_threads")
+        f.restype = ctypes.c_int
+        cores = int(f())
+    if warmup:
+        ctx.step(warmup)
+    p0 = ctx.step_info().total_particle_steps
+    t0 = time.perf_counter()
+    ctx.step(steps)
+    dt = time.perf_counter() - t0
+    info = ctx.step_info()
+    psteps = info.total_particle_steps - p0
+    return psteps / dt, cores, 1e3 * dt / max(steps, 1), info
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
+    if os.path.exists(ref_so):
+        lib_path, prefix, kind = ref_so, "ref_", "reference"
+    else:
+        if not os.path.exists(fast):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_fast.so"], check=True)
+        lib_path, prefix, kind = fast, "orc_", "port"
+    # bounded sample: same scene family, sized so that (K + W) steps take about two minutes on the host cores
+    budget_particle_steps = 120.0 * 4.0e5
+    n_ref = int(min(N_PARTICLES, max(20000, budget_particle_steps / max(args.steps + args.warmup, 1))))
+    scene = make_scene(n_ref)
+    value, cores, ms, info = cpu_arm(lib_path, prefix, scene, args.steps, args.warmup)
+    sample = (f"{args.steps} steps (+{args.warmup} warm-up) of the dam break with {len(scene['fluid'])} fluid particles "
+              f"({'the full workload' if len(scene['fluid']) >= N_PARTICLES * 0.99 else 'same scene family, reduced size'}), FP64, OpenMP")
+    line = {
+        "impl": "reference", "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"synthetic dam break + {N_BOXES} dynamic rigid boxes, {N_PARTICLES} fluid particles per rollout "
+                        f"(BASELINE.json configs[4]); forward step + force/torque Jacobians + sensitivity chain rule",
+            "particles_per_gpu": N_PARTICLES, "rollouts": n_gpus, "parallelism": f"independent rollouts x{n_gpus}",
+            "l2": "working set per step (~0.5 GB of particle state and neighbour lists) exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=N_PARTICLES, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from difffr_b200 import scenes
+    from difffr_b200.cabi import Context
+
+    n_particles = args.particles
+    scene = make_scene(n_particles)
+    ctx = scenes.build_context(lambda **k: Context(device=local_rank, **k), scene, **CFG)
+    nf = ctx.num_fluid
+    dyn = [i for i, b in enumerate(scene["bodies"]) if b["dynamic"]]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps ----
+    ctx.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms0, l0 = ctx.device_time_ms()
+    i0 = ctx.step_info()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.step(args.steps)  # one dfr_step call: K steps enqueued back to back, events on the context's stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    ms1, l1 = ctx.device_time_ms()
+    i1 = ctx.step_info()
+    dev_ms = ms1 - ms0
+    psteps = i1.total_particle_steps - i0.total_particle_steps
+    D = (i1.total_divergence_iterations - i0.total_divergence_iterations) / args.steps
+    P = (i1.total_pressure_iterations - i0.total_pressure_iterations) / args.steps
+    nbar = (i1.total_fluid_neighbors - i0.total_fluid_neighbors) / max(psteps, 1)
+
+    # ---- end to end through the C ABI with host buffers: one "gradient iteration" ----
+    # H2D: the trajectory's initial fluid state (x, v, kappa, kappa_v: 64 B/particle, pinned) + per-step rigid control
+    # input; D2H: per-step rigid state and the eight sensitivity blocks (what the optimisation scripts read per step).
+    x_h = torch.from_numpy(np.ascontiguousarray(scene["fluid"])).pin_memory()
+    v_h = torch.zeros_like(x_h).pin_memory()
+    k_h = torch.zeros(nf, dtype=torch.float64).pin_memory()
+    kv_h = torch.zeros(nf, dtype=torch.float64).pin_memory()
+    e2e_steps = args.steps
+    barrier()
+    t0 = time.perf_counter()
+    ctx.load_fluid_state(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())  # also resets the context
+    d2h = 0
+    for _ in range(e2e_steps):
+        for b in dyn:
+            ctx.set_init_v_omega(b, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0))
+        ctx.step(1)
+        for b in dyn:
+            ctx.body_state(b)
+            for w in range(8):
+                ctx.body_grad(b, w)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    h2d_per_step = (64 * nf) / e2e_steps + 48 * len(dyn)
+    d2h_per_step = len(dyn) * (13 + 4 * 9 + 2 * 12 + 2 * 9) * 8 + 8 * 40
+    e2e_psteps = nf * e2e_steps
+
+    # ---- per-kernel launch durations, live, CUDA events on the context's stream ----
+    ctx.set_profiling(True)
+    ctx.step(max(3, min(10, args.steps)))
+    prof = ctx.kernel_profile()
+    ctx.set_profiling(False)
+    info_p = ctx.step_info()
+
+    # ---- aggregate over ranks: max time, sum of work ----
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = [float(v) for v in t.tolist()]
+        w = torch.tensor([psteps, e2e_psteps, l1 - l0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        psteps_all, e2e_psteps_all, launches_all = [float(v) for v in w.tolist()]
+    else:
+        wall_ms, e2e_ms = wall * 1e3, e2e_wall * 1e3
+        psteps_all, e2e_psteps_all, launches_all = float(psteps), float(e2e_psteps), float(l1 - l0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = psteps_all / (dev_ms * 1e-3)
+    peak, peak_src = load_peaks()
+    # dominant kernel class of the profiled steps
+    classes = {}
+    for name, (ms, n) in prof.items():
+        if name.endswith("(idle)"):
+            continue
+        c = kernel_class(name)
+        a = classes.setdefault(c, [0.0, 0])
+        a[0] += ms
+        a[1] += n
+    total_ms = sum(v[0] for v in classes.values())
+    top = max(classes.items(), key=lambda kv: kv[1][0])
+    top_name, (top_ms, top_n) = top[0], top[1]
+    nf_mean = nbar  # fluid + boundary neighbours per particle
+    bytes_fn = KERNEL_BYTES.get(top_name)
+    if bytes_fn is not None:
+        top_bytes = bytes_fn(nf_mean, 0.0) * nf
+        achieved = top_bytes / (top_ms / top_n * 1e-3) / 1e9
+    else:
+        top_bytes, achieved = None, None
+    step_bytes = algorithmic_bytes_per_particle_step(nbar, D, P)
+    roofline = {
+        "bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "kernel_share_of_step": top_ms / total_ms if total_ms else None,
+        "kernel_avg_ms": top_ms / top_n, "algorithmic_bytes_per_launch": top_bytes,
+        "whole_step": {"bytes_per_particle_step": step_bytes, "achieved": value * step_bytes / 1e9,
+                       "frac": value * step_bytes / 1e9 / peak, "mean_neighbors": nbar, "D": D, "P": P},
+        "kernels_ms_per_step": {k: v[0] / max(3, min(10, args.steps)) for k, v in sorted(classes.items(), key=lambda kv: -kv[1][0])[:8]},
+    }
+    ncu = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu):
+        try:
+            roofline["traffic"] = json.load(open(ncu)).get(top_name)
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+        if os.path.exists(ref_so):
+            lib_path, prefix, kind = ref_so, "ref_", "reference"
+        else:
+            lib_path, prefix, kind = fast, "orc_", "port"
+        if not os.path.exists(lib_path):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_fast.so"], check=True)
+        k_cpu = 6
+        cv, cores, cms, _ = cpu_arm(lib_path, prefix, scene, k_cpu, 1)
+        cpu_baseline = {"value": cv, "unit": "particle-steps/s", "cores": cores, "kind": kind, "ms_per_step": cms,
+                        "sample": f"steps 2..{k_cpu + 1} of the same {nf}-particle scene (1 warm-up step), FP64, OpenMP"}
+
+    line = {
+        "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "solver": {"mean_neighbors": nbar, "divergence_iters": D, "pressure_iters": P, "h": i1.time_step_size},
+        "clocks": clocks,
+        "e2e": {"value": e2e_psteps_all / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_per_step,
+                "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms / e2e_steps,
+                "what": "dfr_load_fluid_state from pinned host arrays + per step: dfr_set_init_v_omega, dfr_step(1), "
+                        "dfr_get_body_state + 8x dfr_get_body_grad per dynamic body"},
+        "gpu_launches": int(launches_all),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,7 @@ SYMBOLS = [
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
     "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
+    "set_profiling", "get_kernel_profile",
 ]
 
 GRAD_NAMES = [
@@ -204,6 +205,9 @@ class Context:
         proto("get_neighbors", C.c_int, vp, C.c_int, C.c_int, ip, ip, i64, C.POINTER(i64))
         proto("add_emitter", C.c_int, vp, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double)
         proto("get_device_time_ms", C.c_int, vp, dp, C.POINTER(i64))
+        if hasattr(L, p + "set_profiling"):  # the CPU oracle has no kernels to profile
+            proto("set_profiling", C.c_int, vp, C.c_int)
+            proto("get_kernel_profile", C.c_int, vp, C.c_int, C.c_char_p, C.c_int, dp, C.POINTER(i64))
         setattr(L, "_dfr_protos_" + p, True)
 
     def default_config(self) -> Config:
@@ -279,6 +283,20 @@ class Context:
         n = C.c_int64(0)
         self._check(self._fn("get_device_time_ms")(self._ctx, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def set_profiling(self, enable=True):
+        self._check(self._fn("set_profiling")(self._ctx, int(bool(enable))))
+
+    def kernel_profile(self):
+        """{kernel name: (total ms, launches)} since profiling was enabled."""
+        rows = {}
+        buf = C.create_string_buffer(256)
+        ms, n = C.c_double(0), C.c_int64(0)
+        i = 0
+        while self._fn("get_kernel_profile")(self._ctx, i, buf, 256, C.byref(ms), C.byref(n)) == 0:
+            rows[buf.value.decode()] = (ms.value, n.value)
+            i += 1
+        return rows
 
     # -- state access ---------------------------------------------------------------------
     @property

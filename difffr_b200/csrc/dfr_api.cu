@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -107,6 +108,23 @@ struct dfr_context {
   double device_ms = 0.0;
   int64_t launches = 0;
   int launch_nf = 0;
+
+  // optional per-kernel timing (dfr_set_profiling): event pairs around every launch on the context's stream
+  struct ProfPending {
+    const char *name;
+    cudaEvent_t e0, e1;
+    int solver;  // -1 none, 0 divergence, 1 pressure
+    int iter;    // iteration index of a speculatively enqueued solver kernel
+  };
+  struct ProfRow {
+    double ms = 0.0;
+    int64_t n = 0;
+  };
+  bool profiling = false;
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::map<std::string, ProfRow> prof_rows;
+  int prof_solver = -1, prof_iter = -1;
 };
 
 namespace {
@@ -123,10 +141,50 @@ int fail(dfr_context *c, int code, const std::string &msg) {
   } while (0)
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+cudaEvent_t prof_event(dfr_context *c) {
+  if (!c->prof_pool.empty()) {
+    cudaEvent_t e = c->prof_pool.back();
+    c->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(dfr_context *c, const char *name) {
+  dfr_context::ProfPending p;
+  p.name = name;
+  p.e0 = prof_event(c);
+  p.e1 = prof_event(c);
+  p.solver = c->prof_solver;
+  p.iter = c->prof_iter;
+  cudaEventRecord(p.e0, c->stream);
+  c->prof_pending.push_back(p);
+}
+void prof_end(dfr_context *c) { cudaEventRecord(c->prof_pending.back().e1, c->stream); }
+// Resolve the pending event pairs (stream must be idle). Solver kernels enqueued speculatively for an
+// iteration the device-side convergence test had already closed are booked under "<name> (idle)".
+void prof_resolve(dfr_context *c, int used_div, int used_prs) {
+  for (auto &p : c->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      std::string key = p.name;
+      if (p.solver >= 0 && p.iter >= (p.solver ? used_prs : used_div)) key += " (idle)";
+      auto &row = c->prof_rows[key];
+      row.ms += ms;
+      row.n += 1;
+    }
+    c->prof_pool.push_back(p.e0);
+    c->prof_pool.push_back(p.e1);
+  }
+  c->prof_pending.clear();
+}
 #define LAUNCH(c, kernel, grid, block, ...)                        \
   do {                                                             \
     if ((grid) > 0) {                                              \
+      if ((c)->profiling) prof_begin((c), #kernel);                \
       kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+      if ((c)->profiling) prof_end((c));                           \
       (c)->launches++;                                             \
     }                                                              \
   } while (0)
@@ -343,13 +401,17 @@ int launch_solver(dfr_context *c) {
   for (;;) {
     spec = std::max(1, std::min(spec, max_it - launched));
     for (int it = 0; it < spec; it++) {
+      c->prof_solver = PRESSURE ? 1 : 0;
+      c->prof_iter = launched + it;
       launch_boundary_side<PRESSURE>(c, true, 1);
       LAUNCH(c, (k_push<PRESSURE, true>), g, 128, PUSH_ARGS);
       LAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, 128, RHO_ARGS);
     }
+    c->prof_solver = -1;
     launched += spec;
     int rc = sync_state(c);
     if (rc) return rc;
+    if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
     const int active = PRESSURE ? c->hSt->prs_active : c->hSt->div_active;
     if (!active || launched >= max_it) break;
     spec = 1;
@@ -542,6 +604,11 @@ void dfr_destroy(dfr_context *c) {
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->woff_f.free(); c->woff_b.free(); c->off_d.free(); c->dP.free(); c->dSt.free();
+  for (auto &p : c->prof_pending) {
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->hSt) cudaFreeHost(c->hSt);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -851,6 +918,7 @@ int dfr_step(dfr_context *c, int n_steps) {
   CU(cudaEventRecord(c->ev1, c->stream));
   int rc = sync_state(c);
   if (rc) return rc;
+  if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -873,6 +941,7 @@ int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -1170,6 +1239,30 @@ int dfr_get_device_time_ms(dfr_context *c, double *total_ms, int64_t *kernel_lau
   if (!c) return DFR_ERR_INVALID;
   if (total_ms) *total_ms = c->device_ms;
   if (kernel_launches) *kernel_launches = c->launches;
+  return DFR_OK;
+}
+
+int dfr_set_profiling(dfr_context *c, int enable) {
+  if (!c) return DFR_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->profiling) prof_resolve(c, 1 << 30, 1 << 30);
+  c->profiling = enable != 0;
+  c->prof_rows.clear();
+  return DFR_OK;
+}
+
+int dfr_get_kernel_profile(dfr_context *c, int index, char *name, int name_capacity, double *total_ms, int64_t *launches) {
+  if (!c) return DFR_ERR_INVALID;
+  if (index < 0 || index >= (int)c->prof_rows.size()) return DFR_ERR_INVALID;
+  auto it = c->prof_rows.begin();
+  std::advance(it, index);
+  if (name && name_capacity > 0) {
+    std::strncpy(name, it->first.c_str(), (size_t)name_capacity - 1);
+    name[name_capacity - 1] = 0;
+  }
+  if (total_ms) *total_ms = it->second.ms;
+  if (launches) *launches = it->second.n;
   return DFR_OK;
 }
 

@@ -197,6 +197,15 @@ int dfr_add_emitter(dfr_context *ctx, int width, int height, const double positi
  * (CUDA events on the context's stream). Replaces Utilities::Timing averages (Timing.h:22-41). */
 int dfr_get_device_time_ms(dfr_context *ctx, double *total_ms, int64_t *kernel_launches);
 
+/* Per-kernel device timing (replaces the START_TIMING/STOP_TIMING_AVG pairs around every phase of
+ * TimeStepDiffDFSPH::step, TimeStepDiffDFSPH.cpp:528-651, and Timing::printAverageTimes, Timing.h:168-196).
+ * While enabled every kernel launch is bracketed by CUDA events on the context's stream; rows are keyed by
+ * kernel name.  Enabling or disabling clears the table.  dfr_get_kernel_profile returns DFR_ERR_INVALID
+ * once index is past the last row. */
+int dfr_set_profiling(dfr_context *ctx, int enable);
+int dfr_get_kernel_profile(dfr_context *ctx, int index, char *name, int name_capacity,
+                           double *total_ms, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif
