@@ -40,12 +40,11 @@ def algorithmic_bytes_per_particle_step(nbar, D, P):
 # algorithmic bytes per fluid particle per launch of each kernel; nf/nb = mean fluid /
 # boundary neighbours per particle of the run
 KERNEL_BYTES = {
-    "k_nbr_count": lambda nf, nb: 32 + 8 + 8.0 / 32,
-    "k_nbr_fill": lambda nf, nb: 32 + 8.0 / 32 + 4 * (nf + nb),
-    "k_density_factor": lambda nf, nb: 32 + 8 + 8 + 8 + 32 + 4 * (nf + nb),
-    "k_rho": lambda nf, nb: 32 + 32 + 8 + 8 + 8 + 8 + 8 + 8 + 4 * (nf + nb),
-    "k_push": lambda nf, nb: 32 + 32 + 32 + 8 + 8 + 8 + 4 + 8 + 4 * (nf + nb),
-    "k_normals": lambda nf, nb: 32 + 8 + 8 + 32 + 4 * nf,
+    "k_nbr_build": lambda nf, nb: 32 + 8 + 4 * (nf + nb),
+    "k_density_factor": lambda nf, nb: 32 + 8 + 8 + 8 + 32 + 32 + 4 * (nf + nb),
+    "k_rho": lambda nf, nb: 32 + 32 + 8 + 8 + 8 + 8 + 8 + 4 + 8 + 32 + 4 * (nf + nb),
+    "k_push": lambda nf, nb: 32 + 32 + 32 + 8 + 8 + 4 + 8 + 4 * (nf + nb),
+    "k_normals": lambda nf, nb: 32 + 4 + 32 + 4 * nf,
     "k_nonpressure": lambda nf, nb: 32 + 32 + 8 + 32 + 8 + 4 + 16 + 32 + 32 + 4 * nf,
     "k_permute_fluid": lambda nf, nb: 4 + 2 * (32 + 32 + 8 + 8 + 4 + 4),
     "k_advect_x": lambda nf, nb: 32 + 32 + 32 + 4 + 16,

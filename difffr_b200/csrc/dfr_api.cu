@@ -61,7 +61,6 @@ struct dfr_context {
   bool finalized = false;
 
   Params P;
-  DevBuf<Params> dP;
   DevBuf<StepState> dSt;
   StepState *hSt = nullptr;  // pinned mirror
 
@@ -77,8 +76,8 @@ struct dfr_context {
   DevBuf<double> kappa[2], kappav[2];
   DevBuf<int> pid[2], pstate[2];
   int cur = 0, vcur = 0;  // current buffer of (pos,kappa,kappav,pid,pstate) / of vel
-  DevBuf<double4> acc, sgp, normal;
-  DevBuf<double> density, factor, dadv, stiff, partials;
+  DevBuf<double4> acc, sgp, normal, xk, xrho;  // xk = (x, stiffness), xrho = (x, density): single-record gathers
+  DevBuf<double> density, factor, dadv, partials;
   // initial state in HBM (id order) restored by dfr_reset
   DevBuf<double4> pos_init, vel_init;
   DevBuf<double> kappa_init, kappav_init;
@@ -100,8 +99,9 @@ struct dfr_context {
   DevBuf<int> cell_of_p, rank_in_cell, sorted_src_f, sorted_src_d, cell_of_b, rank_b;
   // neighbour lists
   DevBuf<int> cnt_f, cnt_b, idx_f, idx_b, idx_d;
-  DevBuf<unsigned int> woff_f, woff_b, off_d;
-  unsigned int cap_f = 0, cap_b = 0, cap_d = 0;
+  DevBuf<unsigned int> off_d;
+  int cap_f = 0, cap_b = 0;  // ELL row capacities (neighbours per particle)
+  unsigned int cap_d = 0;
 
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
@@ -265,15 +265,15 @@ GridView grid_dyn(dfr_context *c) {
 NbrList list_f(dfr_context *c) {
   NbrList l;
   l.cnt = c->cnt_f.p;
-  l.woff = c->woff_f.p;
   l.idx = c->idx_f.p;
+  l.cap = c->cap_f;
   return l;
 }
 NbrList list_b(dfr_context *c) {
   NbrList l;
   l.cnt = c->cnt_b.p;
-  l.woff = c->woff_b.p;
   l.idx = c->idx_b.p;
+  l.cap = c->cap_b;
   return l;
 }
 
@@ -282,7 +282,7 @@ int build_dyn_grid(dfr_context *c) {
   if (c->n_dyn_p == 0) return DFR_OK;
   const int nc = c->P.grid.ncells;
   cudaMemsetAsync(c->cell_start_d.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
-  LAUNCH(c, k_bin_count, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->bpos.p + c->dyn_begin, (const int *)nullptr, c->n_dyn_p,
+  LAUNCH(c, k_bin_count, cdiv(c->n_dyn_p, 128), 128, c->P, c->bpos.p + c->dyn_begin, (const int *)nullptr, c->n_dyn_p,
          c->cell_start_d.p, c->cell_of_b.p, c->rank_b.p);
   int rc = scan_u32(c, c->cell_start_d.p, (size_t)nc + 1, nullptr);
   if (rc) return rc;
@@ -299,7 +299,7 @@ int build_neighbors(dfr_context *c) {
   const int *nf_ptr = &c->dSt.p->nf;
   const int a = c->cur, b = 1 - c->cur;
   cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
-  LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->dP.p, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
+  LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->P, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
   int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
   if (rc) return rc;
   LAUNCH(c, k_bin_scatter, cdiv(n, 128), 128, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p, c->sorted_src_f.p);
@@ -311,23 +311,14 @@ int build_neighbors(dfr_context *c) {
   c->vcur = 1 - c->vcur;
   rc = build_dyn_grid(c);
   if (rc) return rc;
-  const int nw = cdiv(n, 32);
-  cudaMemsetAsync(c->woff_f.p, 0, sizeof(unsigned int) * (nw + 1), c->stream);
-  cudaMemsetAsync(c->woff_b.p, 0, sizeof(unsigned int) * (nw + 1), c->stream);
-  LAUNCH(c, k_nbr_count, cdiv(n, 128), 128, c->dP.p, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
-         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->woff_f.p, c->woff_b.p);
-  rc = scan_u32(c, c->woff_f.p, (size_t)nw + 1, nullptr);
-  if (rc) return rc;
-  rc = scan_u32(c, c->woff_b.p, (size_t)nw + 1, nullptr);
-  if (rc) return rc;
-  LAUNCH(c, k_nbr_fill, cdiv(n, 128), 128, c->dP.p, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
-         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->woff_f.p, c->woff_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
+  LAUNCH(c, k_nbr_build, cdiv(n, 128), 128, c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
-    LAUNCH(c, k_dnbr_count, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
+    LAUNCH(c, k_dnbr_count, cdiv(c->n_dyn_p, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
     rc = scan_u32(c, c->off_d.p, (size_t)c->n_dyn_p + 1, nullptr);
     if (rc) return rc;
-    LAUNCH(c, k_dnbr_fill, cdiv(c->n_dyn_p, 128), 128, c->dP.p, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
+    LAUNCH(c, k_dnbr_fill, cdiv(c->n_dyn_p, 128), 128, c->P, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
            c->off_d.p, c->idx_d.p, c->cap_d);
   }
   return DFR_OK;
@@ -335,7 +326,7 @@ int build_neighbors(dfr_context *c) {
 
 int compute_boundary_volumes(dfr_context *c) {
   if (c->n_b == 0) return DFR_OK;
-  LAUNCH(c, k_boundary_volume, cdiv(c->n_b, 128), 128, c->dP.p, c->bpos.p, c->n_b, c->n_static_p, grid_static(c), grid_dyn(c),
+  LAUNCH(c, k_boundary_volume, cdiv(c->n_b, 128), 128, c->P, c->bpos.p, c->n_b, c->n_static_p, grid_static(c), grid_dyn(c),
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->bvol.p);
   LAUNCH(c, k_store_volume, cdiv(c->n_b, 128), 128, c->bpos.p, c->bvol.p, c->n_b);
   return DFR_OK;
@@ -346,7 +337,7 @@ int sync_state(dfr_context *c) {
   CU(cudaStreamSynchronize(c->stream));
   if (c->hSt->error_flags) {
     char buf[160];
-    std::snprintf(buf, sizeof(buf), "neighbour list capacity exceeded (flags %d; used f=%u b=%u d=%u, cap f=%u b=%u d=%u)",
+    std::snprintf(buf, sizeof(buf), "neighbour list capacity exceeded (flags %d; longest rows f=%u b=%u, d entries=%u; cap f=%d b=%d d=%u)",
                   c->hSt->error_flags, c->hSt->list_used_f, c->hSt->list_used_b, c->hSt->list_used_d, c->cap_f, c->cap_b, c->cap_d);
     return fail(c, DFR_ERR_CAPACITY, buf);
   }
@@ -359,8 +350,8 @@ void launch_boundary_side(dfr_context *c, bool grad, int iter_kernel) {
   const int g = c->n_acc_blocks, t = BS_WARPS * 32;
   const int a = c->cur;
 #define BS_ARGS                                                                                                               \
-  c->dP.p, c->dSt.p, c->dBodies.p, c->blk_body.p, c->blk_first.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p,         \
-      c->bx0.p, c->dyn_begin, c->off_d.p, c->idx_d.p, c->stiff.p, c->dadv.p, c->factor.p, c->sgp.p, c->pstate[a].p, iter_kernel, \
+  c->P, c->dSt.p, c->dBodies.p, c->blk_body.p, c->blk_first.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p,         \
+      c->bx0.p, c->dyn_begin, c->off_d.p, c->idx_d.p, c->dadv.p, c->factor.p, c->sgp.p, c->pstate[a].p, iter_kernel, \
       c->acc_rows.p
   if (grad) {
     if (PRESSURE)
@@ -386,9 +377,9 @@ int launch_solver(dfr_context *c) {
   const bool warm = PRESSURE ? c->cfg.use_pressure_warmstart : c->cfg.use_divergence_warmstart;
   double *kap = PRESSURE ? c->kappa[a].p : c->kappav[a].p;
 #define RHO_ARGS                                                                                                             \
-  c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
-      c->pstate[a].p, kap, c->dadv.p, c->stiff.p, c->partials.p
-#define PUSH_ARGS c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->stiff.p, c->pstate[a].p, kap, warm ? 1 : 0
+  c->P, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
+      c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p
+#define PUSH_ARGS c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0
   if (warm) {
     LAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, 128, RHO_ARGS);
     launch_boundary_side<PRESSURE>(c, false, 0);
@@ -429,13 +420,12 @@ int launch_solver(dfr_context *c) {
 // one SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169)
 int launch_step(dfr_context *c) {
   const int n = c->launch_nf, g = cdiv(n, 128);
-  LAUNCH(c, k_begin_step, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p);
+  LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p);
   int rc = build_neighbors(c);
   if (rc) return rc;
-  LAUNCH(c, k_sum_counts, g, 128, c->dSt.p, c->cnt_f.p, c->cnt_b.p);
   int a = c->cur;
-  LAUNCH(c, k_density_factor, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
-         c->sgp.p);
+  LAUNCH(c, k_density_factor, g, 128, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
+         c->sgp.p, c->xrho.p);
   bool scale_kv = false;
   if (c->cfg.enable_divergence_solver) {
     rc = launch_solver<false>(c);
@@ -443,24 +433,24 @@ int launch_step(dfr_context *c) {
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
   if (c->cfg.surface_tension_method == 2)
-    LAUNCH(c, k_normals, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, list_f(c), c->density.p, c->normal.p);
-  LAUNCH(c, k_nonpressure, g, 128, c->dP.p, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+    LAUNCH(c, k_normals, g, 128, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
+  LAUNCH(c, k_nonpressure, g, 128, c->P, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
          c->density.p, c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
   c->vcur = 1 - c->vcur;
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
-  LAUNCH(c, k_cfl_finish, 1, 32, c->dP.p, c->dSt.p);
+  LAUNCH(c, k_cfl_finish, 1, 32, c->P, c->dSt.p);
   rc = launch_solver<true>(c);
   if (rc) return rc;
   LAUNCH(c, k_advect_x, g, 128, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->pstate[a].p, c->kappa[a].p,
          c->cfg.use_pressure_warmstart ? 1 : 0);
   if (c->P.n_bodies > 0) {
     LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
-    LAUNCH(c, k_body_update, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p, c->dMgr.p);
+    LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p);
     if (c->n_dyn_p > 0)
       LAUNCH(c, k_update_boundary_particles, cdiv(c->n_dyn_p, 128), 128, c->dBodies.p, c->bbody.p, c->bx0.p, c->bpos.p, c->bvel.p,
              c->dyn_begin, c->n_dyn_p, 0);
   } else {
-    LAUNCH(c, k_body_update, 1, 32, c->dP.p, c->dSt.p, c->dBodies.p, c->dMgr.p);
+    LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p);
   }
   return DFR_OK;
 }
@@ -596,14 +586,14 @@ void dfr_destroy(dfr_context *c) {
   for (int k = 0; k < 2; k++) {
     c->pos[k].free(); c->vel[k].free(); c->kappa[k].free(); c->kappav[k].free(); c->pid[k].free(); c->pstate[k].free();
   }
-  c->acc.free(); c->sgp.free(); c->normal.free(); c->density.free(); c->factor.free(); c->dadv.free(); c->stiff.free();
+  c->acc.free(); c->sgp.free(); c->normal.free(); c->density.free(); c->factor.free(); c->dadv.free(); c->xk.free(); c->xrho.free();
   c->partials.free(); c->pos_init.free(); c->vel_init.free(); c->kappa_init.free(); c->kappav_init.free();
   c->bpos.free(); c->bvel.free(); c->bx0.free(); c->bpos_tmp.free(); c->bx0_tmp.free(); c->bbody.free(); c->borig.free();
   c->bbody_tmp.free(); c->borig_tmp.free(); c->bvol.free(); c->dBodies.free(); c->dMgr.free(); c->acc_rows.free();
   c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
-  c->woff_f.free(); c->woff_b.free(); c->off_d.free(); c->dP.free(); c->dSt.free();
+  c->off_d.free(); c->dSt.free();
   for (auto &p : c->prof_pending) {
     cudaEventDestroy(p.e0);
     cudaEventDestroy(p.e1);
@@ -780,14 +770,13 @@ int dfr_finalize(dfr_context *c) {
   const size_t N = (size_t)std::max<int64_t>(c->nf_cap, 1);
   c->launch_nf = (int)c->nf0;
   const int nc = P.grid.ncells;
-  CU(c->dP.alloc(1));
   CU(c->dSt.alloc(1));
   for (int k = 0; k < 2; k++) {
     CU(c->pos[k].alloc(N)); CU(c->vel[k].alloc(N)); CU(c->kappa[k].alloc(N)); CU(c->kappav[k].alloc(N));
     CU(c->pid[k].alloc(N)); CU(c->pstate[k].alloc(N));
   }
   CU(c->acc.alloc(N)); CU(c->sgp.alloc(N)); CU(c->normal.alloc(N)); CU(c->density.alloc(N)); CU(c->factor.alloc(N));
-  CU(c->dadv.alloc(N)); CU(c->stiff.alloc(N)); CU(c->partials.alloc(N / 128 + 2));
+  CU(c->dadv.alloc(N)); CU(c->xk.alloc(N)); CU(c->xrho.alloc(N)); CU(c->partials.alloc(N / 128 + 2));
   CU(c->pos_init.alloc(N)); CU(c->vel_init.alloc(N)); CU(c->kappa_init.alloc(N)); CU(c->kappav_init.alloc(N));
   const size_t NB = (size_t)std::max(c->n_b, 1);
   CU(c->bpos.alloc(NB)); CU(c->bvel.alloc(NB)); CU(c->bx0.alloc(NB)); CU(c->bbody.alloc(NB)); CU(c->borig.alloc(NB));
@@ -795,20 +784,21 @@ int dfr_finalize(dfr_context *c) {
   CU(c->dBodies.alloc(std::max<size_t>(c->bodies.size(), 1)));
   CU(c->dMgr.alloc(std::max<size_t>(c->bodies.size() * c->bodies.size(), 1)));
   CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
-  const size_t max_scan = std::max<size_t>((size_t)nc + 1, std::max<size_t>(N / 32 + 2, (size_t)c->n_dyn_p + 1));
+  const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
   CU(c->cell_of_p.alloc(N)); CU(c->rank_in_cell.alloc(N)); CU(c->sorted_src_f.alloc(N));
   const size_t ND = (size_t)std::max(c->n_dyn_p, 1), NS = (size_t)std::max(c->n_static_p, 1);
   CU(c->sorted_src_d.alloc(std::max(ND, NS))); CU(c->cell_of_b.alloc(std::max(ND, NS))); CU(c->rank_b.alloc(std::max(ND, NS)));
-  CU(c->cnt_f.alloc(N)); CU(c->cnt_b.alloc(N)); CU(c->woff_f.alloc(N / 32 + 2)); CU(c->woff_b.alloc(N / 32 + 2));
-  const int per_f = cfg.reserved_i[0] > 0 ? cfg.reserved_i[0] : 80;
-  const int per_b = cfg.reserved_i[1] > 0 ? cfg.reserved_i[1] : 48;
+  CU(c->cnt_f.alloc(N)); CU(c->cnt_b.alloc(N));
+  // ELL capacities: neighbours per particle (support 4r, spacing 2r: ~30 at rest, more under compression).  Slots
+  // beyond a row's count are never touched, so generous capacities cost address space, not bandwidth.
+  c->cap_f = cfg.reserved_i[0] > 0 ? cfg.reserved_i[0] : 96;
+  c->cap_b = cfg.reserved_i[1] > 0 ? cfg.reserved_i[1] : 64;
   const int per_d = cfg.reserved_i[2] > 0 ? cfg.reserved_i[2] : 96;
-  const size_t cf = std::min<size_t>((N + 32) * (size_t)per_f, 0xfffffff0u), cb = std::min<size_t>((N + 32) * (size_t)per_b, 0xfffffff0u);
-  c->cap_f = (unsigned int)cf;
-  c->cap_b = (unsigned int)cb;
   c->cap_d = (unsigned int)(ND * per_d);
-  CU(c->idx_f.alloc(c->cap_f)); CU(c->idx_b.alloc(c->cap_b)); CU(c->idx_d.alloc(c->cap_d)); CU(c->off_d.alloc(ND + 1));
+  const size_t nwarp = (N + 31) / 32;
+  CU(c->idx_f.alloc(nwarp * 32 * (size_t)c->cap_f)); CU(c->idx_b.alloc(nwarp * 32 * (size_t)c->cap_b));
+  CU(c->idx_d.alloc(c->cap_d)); CU(c->off_d.alloc(ND + 1));
 
   // ---- accumulator blocks of the boundary-side kernel: one body per block ----
   std::vector<int> blk_body, blk_first;
@@ -833,7 +823,6 @@ int dfr_finalize(dfr_context *c) {
   }
 
   // ---- uploads ----
-  CU(cudaMemcpy(c->dP.p, &P, sizeof(P), cudaMemcpyHostToDevice));
   if (c->nf0) {
     std::vector<double4> p4(c->nf0), v4(c->nf0);
     for (int64_t i = 0; i < c->nf0; i++) {
@@ -855,7 +844,7 @@ int dfr_finalize(dfr_context *c) {
     const int ns = c->n_static_p;
     CU(c->bpos_tmp.alloc(ns)); CU(c->bx0_tmp.alloc(ns)); CU(c->bbody_tmp.alloc(ns)); CU(c->borig_tmp.alloc(ns));
     CU(cudaMemsetAsync(c->cell_start_s.p, 0, sizeof(unsigned int) * (nc + 1), c->stream));
-    LAUNCH(c, k_bin_count, cdiv(ns, 128), 128, c->dP.p, c->bpos.p, (const int *)nullptr, ns, c->cell_start_s.p, c->cell_of_b.p,
+    LAUNCH(c, k_bin_count, cdiv(ns, 128), 128, c->P, c->bpos.p, (const int *)nullptr, ns, c->cell_start_s.p, c->cell_of_b.p,
            c->rank_b.p);
     int rc = scan_u32(c, c->cell_start_s.p, (size_t)nc + 1, nullptr);
     if (rc) return rc;
@@ -1186,18 +1175,17 @@ int dfr_get_neighbors(dfr_context *c, int set_a, int set_b, int32_t *counts, int
     const bool fluid = (set_b == -1);
     rows.assign(n, {});
     if (n) {
-      const int nw = (n + 31) / 32;
+      const size_t nw = ((size_t)n + 31) / 32;
+      const size_t cap = fluid ? c->cap_f : c->cap_b;
       std::vector<int> cnt(n);
-      std::vector<unsigned int> woff(nw + 1);
       CU(cudaMemcpy(cnt.data(), fluid ? c->cnt_f.p : c->cnt_b.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-      CU(cudaMemcpy(woff.data(), fluid ? c->woff_f.p : c->woff_b.p, (nw + 1) * sizeof(unsigned int), cudaMemcpyDeviceToHost));
-      std::vector<int> idx(std::max<size_t>(woff[nw], 1));
-      if (woff[nw]) CU(cudaMemcpy(idx.data(), fluid ? c->idx_f.p : c->idx_b.p, (size_t)woff[nw] * sizeof(int), cudaMemcpyDeviceToHost));
+      std::vector<int> idx(nw * 32 * cap);
+      CU(cudaMemcpy(idx.data(), fluid ? c->idx_f.p : c->idx_b.p, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
       const HostBody *hb = fluid ? nullptr : &c->bodies[set_b];
       for (int i = 0; i < n; i++) {
         std::vector<int32_t> &r = rows[ids[i]];
         for (int k = 0; k < cnt[i]; k++) {
-          const int j = idx[(size_t)woff[i >> 5] + (size_t)k * 32 + (i & 31)];
+          const int j = idx[((size_t)(i >> 5) * cap + (size_t)k) * 32 + (i & 31)];
           if (fluid)
             r.push_back(ids[j]);
           else {

@@ -11,11 +11,23 @@ namespace dfr {
 #define DFR_EPS 1.0e-5  // m_eps, TimeStepDiffDFSPH.h:26
 #define DFR_FULL 0xffffffffu
 
-// read-only 32-byte record load (two 128-bit LDG.NC on the same sector)
+// read-only 32-byte record load as ONE 256-bit instruction (sm_100: LDG.E.ENL2.256.CONSTANT).  A gathered
+// record then costs one L1 tag/data wavefront per distinct 128-byte line instead of two (profiles/r1a: the
+// neighbour passes are bound by L1 data-stage wavefronts, not by HBM or the FP64 pipe).
 __device__ __forceinline__ double4 ldg4(const double4 *p) {
-  const double2 *q = reinterpret_cast<const double2 *>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+// 256-bit store of one record (STG.E.ENL2.256)
+__device__ __forceinline__ void stg4(double4 *p, const double4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+// plain (coherent) 256-bit load of a record this kernel family also writes
+__device__ __forceinline__ double4 ld4(const double4 *p) {
+  double4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -243,9 +255,8 @@ __global__ void k_scan_add(unsigned int *out, const unsigned int *tile_sums, siz
 // cell binning / counting sort (replaces CompactNSearch's hash-grid build; call site
 // Simulation.cpp:746 find_neighbors, and z_sort Simulation.cpp:755)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_bin_count(const Params *Pp, const double4 *pos, const int *n_ptr, int n_fixed, unsigned int *cell_count,
+__global__ void k_bin_count(const __grid_constant__ Params P, const double4 *pos, const int *n_ptr, int n_fixed, unsigned int *cell_count,
                             int *cell_of_particle, int *rank_in_cell) {
-  const Params &P = *Pp;
   const int n = n_ptr ? *n_ptr : n_fixed;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -366,73 +377,49 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
     }
 }
 
-// pass 1: counts (fluid->fluid, fluid->boundary) and the per-warp slice size 32 * max(count)
-__global__ void __launch_bounds__(128) k_nbr_count(const Params *Pp, const StepState *st, const double4 *pos, GridView gf, GridView gs,
-                                                    GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
-                                                    unsigned int *wsize_f, unsigned int *wsize_b) {
-  const Params &P = *Pp;
+// Single scan: fluid->fluid and fluid->boundary neighbour lists in a warp-interleaved ELL layout
+// (slot k of sorted particle i at idx[((i >> 5) * cap + k) * 32 + (i & 31)]: a warp reads 128 contiguous
+// bytes per k, and no count pass / prefix sum is needed).  Rows longer than cap raise error_flags; the
+// host then grows the capacity and replays the step (dfr_api.cu: launch_step).
+__global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
+                                                    GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
+                                                    int *idx_f, int *idx_b, int cap_f, int cap_b) {
   const int n = st->nf;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int cf = 0, cb = 0;
   if (i < n) {
+    const int lane = i & 31;
     const double4 p = pos[i];
-    for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int) { cf++; });
-    if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int) { cb++; });
-    if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int) { cb++; });
-    cnt_f[i] = cf;
-    cnt_b[i] = cb;
-  }
-  const int mf = __reduce_max_sync(DFR_FULL, cf);
-  const int mb = __reduce_max_sync(DFR_FULL, cb);
-  if ((threadIdx.x & 31) == 0 && (i < n)) {
-    wsize_f[i >> 5] = 32u * (unsigned int)mf;
-    wsize_b[i >> 5] = 32u * (unsigned int)mb;
-  }
-}
-// pass 2: fill the warp-interleaved lists
-__global__ void __launch_bounds__(128) k_nbr_fill(const Params *Pp, StepState *st, const double4 *pos, GridView gf, GridView gs, GridView gd,
-                                                   int has_static, int has_dyn, const unsigned int *woff_f, const unsigned int *woff_b,
-                                                   int *idx_f, int *idx_b, unsigned int cap_f, unsigned int cap_b) {
-  const Params &P = *Pp;
-  const int n = st->nf;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int lane = i & 31, w = i >> 5;
-  const int nw = (n + 31) >> 5;
-  const double4 p = pos[i];
-  // woff has nw + 1 entries (exclusive scan incl. total)
-  const bool ok_f = woff_f[w + 1] <= cap_f;
-  const bool ok_b = woff_b[w + 1] <= cap_b;
-  if (!ok_f) atomicOr(&st->error_flags, 1);
-  if (!ok_b) atomicOr(&st->error_flags, 2);
-  if (i == 0) {
-    st->list_used_f = woff_f[nw];
-    st->list_used_b = woff_b[nw];
-  }
-  if (ok_f) {
-    int *o = idx_f + woff_f[w] + lane;
-    int k = 0;
+    int *of = idx_f + ((size_t)(i >> 5) * cap_f) * 32 + lane;
+    int *ob = idx_b + ((size_t)(i >> 5) * cap_b) * 32 + lane;
     for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int j) {
-      o[(size_t)k * 32] = j;
-      k++;
+      if (cf < cap_f) of[(size_t)cf * 32] = j;
+      cf++;
     });
-  }
-  if (ok_b) {
-    int *o = idx_b + woff_b[w] + lane;
-    int k = 0;
     if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int j) {
-      o[(size_t)k * 32] = j;
-      k++;
+      if (cb < cap_b) ob[(size_t)cb * 32] = j;
+      cb++;
     });
     if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int j) {
-      o[(size_t)k * 32] = j;
-      k++;
+      if (cb < cap_b) ob[(size_t)cb * 32] = j;
+      cb++;
     });
+    if (cf > cap_f) atomicOr(&st->error_flags, 1);
+    if (cb > cap_b) atomicOr(&st->error_flags, 2);
+    cnt_f[i] = min(cf, cap_f);
+    cnt_b[i] = min(cb, cap_b);
+  }
+  // neighbour statistics of the step (mean neighbour count feeds the roofline's algorithmic bytes)
+  const int tot = __reduce_add_sync(DFR_FULL, cf + cb);
+  const int mf = __reduce_max_sync(DFR_FULL, cf), mb = __reduce_max_sync(DFR_FULL, cb);
+  if ((threadIdx.x & 31) == 0 && tot) {
+    atomicAdd((unsigned long long *)&st->total_neighbors, (unsigned long long)tot);
+    if ((unsigned int)mf > st->list_used_f) atomicMax(&st->list_used_f, (unsigned int)mf);
+    if ((unsigned int)mb > st->list_used_b) atomicMax(&st->list_used_b, (unsigned int)mb);
   }
 }
 // dynamic boundary particle -> fluid neighbours, CSR rows (one warp later walks one row)
-__global__ void __launch_bounds__(128) k_dnbr_count(const Params *Pp, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf, unsigned int *cnt_d) {
-  const Params &P = *Pp;
+__global__ void __launch_bounds__(128) k_dnbr_count(const __grid_constant__ Params P, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf, unsigned int *cnt_d) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_dyn) return;
   const double4 p = bpos[dyn_begin + t];
@@ -440,9 +427,8 @@ __global__ void __launch_bounds__(128) k_dnbr_count(const Params *Pp, const doub
   for_each_in_range(P, gf, p.x, p.y, p.z, -1, [&](int) { c++; });
   cnt_d[t] = c;
 }
-__global__ void __launch_bounds__(128) k_dnbr_fill(const Params *Pp, StepState *st, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf,
+__global__ void __launch_bounds__(128) k_dnbr_fill(const __grid_constant__ Params P, StepState *st, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf,
                                                     const unsigned int *off_d, int *idx_d, unsigned int cap_d) {
-  const Params &P = *Pp;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_dyn) return;
   if (off_d[t + 1] > cap_d) {
@@ -459,9 +445,8 @@ __global__ void __launch_bounds__(128) k_dnbr_fill(const Params *Pp, StepState *
 // boundary volume psi (Simulation::updateBoundaryVolume, Simulation.cpp:831-902;
 // BoundaryModel_Akinci2012::computeBoundaryVolume, BoundaryModel_Akinci2012.cpp:257-284)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_boundary_volume(const Params *Pp, double4 *bpos, int n_b, int n_static, GridView gs, GridView gd,
+__global__ void __launch_bounds__(128) k_boundary_volume(const __grid_constant__ Params P, double4 *bpos, int n_b, int n_static, GridView gs, GridView gd,
                                                           int has_static, int has_dyn, double *vol_out) {
-  const Params &P = *Pp;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_b) return;
   const double4 p = bpos[b];
@@ -491,19 +476,17 @@ __global__ void k_store_volume(double4 *bpos, const double *vol, int n_b) {
 // density + DFSPH factor, fused (TimeStep::computeDensities, TimeStep.cpp:147-200;
 // computeDFSPHFactor, TimeStepDiffDFSPH.cpp:883-962)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_density_factor(const Params *Pp, const StepState *st, const double4 *pos, const double4 *bpos,
-                                                         NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp) {
-  const Params &P = *Pp;
+__global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ Params P, const StepState *st, const double4 *pos, const double4 *bpos,
+                                                         NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp, double4 *xrho) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->nf) return;
   const double4 pi = pos[i];
-  const int lane = i & 31, w = i >> 5;
   double dens = P.volume * P.W_zero;
   double S = 0.0;
   d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij
   {
     const int n = lf.cnt[i];
-    const int *o = lf.idx + lf.woff[w] + lane;
+    const int *o = nbr_row(lf, i);
     for (int k = 0; k < n; k++) {
       const int j = o[(size_t)k * 32];
       const double4 pj = ldg4(pos + j);
@@ -518,7 +501,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const Params *Pp, const 
   }
   {
     const int n = lb.cnt[i];
-    const int *o = lb.idx + lb.woff[w] + lane;
+    const int *o = nbr_row(lb, i);
     for (int k = 0; k < n; k++) {
       const int j = o[(size_t)k * 32];
       const double4 pj = ldg4(bpos + j);
@@ -530,6 +513,8 @@ __global__ void __launch_bounds__(128) k_density_factor(const Params *Pp, const 
     }
   }
   density[i] = dens * P.density0;
+  // (x, rho) record: k_normals gathers position and density of a neighbour in one 256-bit load
+  stg4(xrho + i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
   const double denom = S + dot(G, G);
   factor[i] = (denom > DFR_EPS) ? -1.0 / denom : 0.0;
   sgp[i] = make_double4(-G.x, -G.y, -G.z, 0.0);
@@ -543,10 +528,9 @@ __global__ void __launch_bounds__(128) k_density_factor(const Params *Pp, const 
 enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
 
 template <bool PRESSURE, int MODE>
-__global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(128) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
-                                              const int *state, double *kappa, double *dadv, double *stiff, double *partials) {
-  const Params &P = *Pp;
+                                              const int *state, double *kappa, double *dadv, double4 *xk, double *partials) {
   if (MODE == RHO_ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
@@ -557,11 +541,10 @@ __global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, co
   if (i < nf) {
     const double4 pi = pos[i];
     const double4 vi = vel[i];
-    const int lane = i & 31, w = i >> 5;
-    double delta = 0.0;
+      double delta = 0.0;
     const int nF = lf.cnt[i];
     {
-      const int *o = lf.idx + lf.woff[w] + lane;
+      const int *o = nbr_row(lf, i);
       for (int k = 0; k < nF; k++) {
         const int j = o[(size_t)k * 32];
         const double4 pj = ldg4(pos + j);
@@ -573,7 +556,7 @@ __global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, co
     }
     const int nB = lb.cnt[i];
     {
-      const int *o = lb.idx + lb.woff[w] + lane;
+      const int *o = nbr_row(lb, i);
       for (int k = 0; k < nB; k++) {
         const int j = o[(size_t)k * 32];
         const double4 pj = ldg4(bpos + j);
@@ -601,10 +584,12 @@ __global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, co
         kap = (rho > 0.0) ? 0.5 * fmax(kappa[i], -0.5) / h : 0.0;
       if (state[i] != 0) kap = 0.0;  // the reference zeroes these in its second loop (:1008-1012 / :1737-1741)
       kappa[i] = kap;
-      stiff[i] = kap;
+      stg4(xk + i, make_double4(pi.x, pi.y, pi.z, kap));
     } else {
       const double b = PRESSURE ? rho - 1.0 : rho;
-      stiff[i] = PRESSURE ? b * factor[i] / (h * h) : b * factor[i] / h;
+      const double ks = PRESSURE ? b * factor[i] / (h * h) : b * factor[i] / h;
+      // (x, k) record: the push and the boundary-side kernel gather position and stiffness together
+      stg4(xk + i, make_double4(pi.x, pi.y, pi.z, ks));
     }
   }
   if (MODE == RHO_ITER) {
@@ -665,9 +650,8 @@ __global__ void __launch_bounds__(128) k_rho(const Params *Pp, StepState *st, co
 // (k_boundary_side) instead of being scattered from here.
 // ---------------------------------------------------------------------------------------------
 template <bool PRESSURE, bool ITER>
-__global__ void __launch_bounds__(128) k_push(const Params *Pp, const StepState *st, const double4 *pos, double4 *vel, const double4 *bpos,
-                                               NbrList lf, NbrList lb, const double *stiff, const int *state, double *kappa, int accumulate_kappa) {
-  const Params &P = *Pp;
+__global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
+                                               NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa) {
   if (ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
@@ -675,20 +659,19 @@ __global__ void __launch_bounds__(128) k_push(const Params *Pp, const StepState 
   if (i >= st->nf) return;
   if (state[i] != 0) return;
   const double h = PRESSURE ? st->h : st->h_step;
-  const double ki = stiff[i];
+  const double4 pi = xk[i];
+  const double ki = pi.w;
   if (ITER && accumulate_kappa) kappa[i] += ki;
-  const double4 pi = pos[i];
   double4 v = vel[i];
-  const int lane = i & 31, w = i >> 5;
   d3 dv = mk3(0, 0, 0);
   {
     const int n = lf.cnt[i];
-    const int *o = lf.idx + lf.woff[w] + lane;
+    const int *o = nbr_row(lf, i);
     for (int k = 0; k < n; k++) {
       const int j = o[(size_t)k * 32];
-      const double kSum = ki + __ldg(stiff + j);
+      const double4 pj = ldg4(xk + j);
+      const double kSum = ki + pj.w;
       if (fabs(kSum) > DFR_EPS) {
-        const double4 pj = ldg4(pos + j);
         const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
         const double c = cubic_grad_coeff(P, dot(r, r));
         // vel -= h * kSum * (-V gradW)
@@ -698,7 +681,7 @@ __global__ void __launch_bounds__(128) k_push(const Params *Pp, const StepState 
   }
   if (fabs(ki) > DFR_EPS) {
     const int n = lb.cnt[i];
-    const int *o = lb.idx + lb.woff[w] + lane;
+    const int *o = nbr_row(lb, i);
     for (int k = 0; k < n; k++) {
       const int j = o[(size_t)k * 32];
       const double4 pj = ldg4(bpos + j);
@@ -724,13 +707,12 @@ __global__ void __launch_bounds__(128) k_push(const Params *Pp, const StepState 
 #define BS_PART_PER_BLOCK 32  // boundary particles per block (8 per warp)
 
 template <int MODE /*0 pressure, 1 divergence*/, bool GRAD>
-__global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const Params *Pp, const StepState *st, const BodyDev *bodies, const int *blk_body,
-                                                                  const int *blk_first, const double4 *pos, const double4 *vel,
+__global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_constant__ Params P, const StepState *st, const BodyDev *bodies, const int *blk_body,
+                                                                  const int *blk_first, const double4 *xk, const double4 *vel,
                                                                   const double4 *bpos, const double4 *bvel, const double4 *bx0,
                                                                   int dyn_begin, const unsigned int *off_d, const int *idx_d,
-                                                                  const double *stiff, const double *dadv, const double *factor,
+                                                                  const double *dadv, const double *factor,
                                                                   const double4 *sgp, const int *state, int iter_kernel, double *acc_rows) {
-  const Params &P = *Pp;
   if (iter_kernel) {
     if (!(MODE == 0 ? st->prs_active : st->div_active)) return;
   }
@@ -760,10 +742,10 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const Params *P
     }
     for (int p = s + lane; p < e; p += 32) {
       const int i = idx_d[p];
-      const double4 pi = ldg4(pos + i);
+      const double4 pi = ldg4(xk + i);
       const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
       // real reaction force of the push that follows: F = -m dv / dt = m k_i g, g = -V_j gradW
-      const double ki_real = __ldg(stiff + i);
+      const double ki_real = pi.w;
       if (!do_grad) {
         if (__ldg(state + i) == 0 && fabs(ki_real) > DFR_EPS) {
           const double c = cubic_grad_coeff(P, dot(r, r));
@@ -920,32 +902,29 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const Params *P
 // clearAccelerations (TimeStep.cpp:66-81), v += h a (TimeStepDiffDFSPH.cpp:589-604) and the CFL
 // maximum (Simulation.cpp:542-575), fused.  kappa_v *= h_step of divergenceSolve (:870-880) rides along.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_normals(const Params *Pp, const StepState *st, const double4 *pos, NbrList lf, const double *density,
+__global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params P, const StepState *st, const double4 *xrho, NbrList lf,
                                                   double4 *normal) {
-  const Params &P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->nf) return;
-  const double4 pi = pos[i];
-  const int lane = i & 31, w = i >> 5;
+  const double4 pi = xrho[i];
   d3 n = mk3(0, 0, 0);
   const int cnt = lf.cnt[i];
-  const int *o = lf.idx + lf.woff[w] + lane;
+  const int *o = nbr_row(lf, i);
   for (int k = 0; k < cnt; k++) {
     const int j = o[(size_t)k * 32];
-    const double4 pj = ldg4(pos + j);
+    const double4 pj = ldg4(xrho + j);
     const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
     const double c = cubic_grad_coeff(P, dot(r, r));
-    n += (P.mass / __ldg(density + j) * c) * r;
+    n += (P.mass / pj.w * c) * r;
   }
   // w carries the particle's density so that the force pass gathers (n_j, rho_j) in one record
-  normal[i] = make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, density[i]);
+  stg4(normal + i, make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, pi.w));
 }
 
-__global__ void __launch_bounds__(128) k_nonpressure(const Params *Pp, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                                       const double4 *bvel, NbrList lf, NbrList lb, const double *density,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
                                                       double4 *acc_out, double4 *vel_out) {
-  const Params &P = *Pp;
   const int nf = st->nf;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double h = st->h_step;
@@ -953,8 +932,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const Params *Pp, StepState
   if (i < nf) {
     const double4 pi = pos[i];
     const double4 vi = vel[i];
-    const int lane = i & 31, w = i >> 5;
-    d3 a = mk3(P.gx, P.gy, P.gz);
+      d3 a = mk3(P.gx, P.gy, P.gz);
     const double rhoi = density[i];
     const bool st_on = (P.st_method == 2);
     const bool visc_on = (P.visc_method == 1);
@@ -966,7 +944,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const Params *Pp, StepState
     const double h2s = P.support_radius * P.support_radius;
     {
       const int cnt = lf.cnt[i];
-      const int *o = lf.idx + lf.woff[w] + lane;
+      const int *o = nbr_row(lf, i);
       for (int k = 0; k < cnt; k++) {
         const int j = o[(size_t)k * 32];
         const double4 pj = ldg4(pos + j);
@@ -995,7 +973,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const Params *Pp, StepState
       // boundary adhesion / boundary viscosity: zero coefficients in every shipped scene; the
       // reaction force of the boundary-viscosity term on dynamic bodies is not carried here.
       const int cnt = lb.cnt[i];
-      const int *o = lb.idx + lb.woff[w] + lane;
+      const int *o = nbr_row(lb, i);
       for (int k = 0; k < cnt; k++) {
         const int j = o[(size_t)k * 32];
         const double4 pj = ldg4(bpos + j);
@@ -1045,8 +1023,7 @@ __global__ void k_cfl_boundary(StepState *st, const double4 *bvel, int dyn_begin
 }
 
 // Simulation::updateTimeStepSize (Simulation.cpp:524-616) + solver-control reset for the pressure solve
-__global__ void k_cfl_finish(const Params *Pp, StepState *st) {
-  const Params &P = *Pp;
+__global__ void k_cfl_finish(const __grid_constant__ Params P, StepState *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // close the divergence solve bookkeeping
   st->last_iters_v = st->div_iters;
@@ -1087,16 +1064,6 @@ __global__ void k_advect_x(const StepState *st, double4 *pos, const double4 *vel
     pos[i] = p;
   }
   if (scale_kappa) kappa[i] *= st->h * st->h;
-}
-
-__global__ void k_sum_counts(StepState *st, const int *cnt_f, const int *cnt_b) {
-  // neighbour statistics of the step (mean neighbour count feeds the roofline's algorithmic bytes)
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  long long c = 0;
-  if (i < st->nf) c = (long long)cnt_f[i] + cnt_b[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(DFR_FULL, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long *)&st->total_neighbors, (unsigned long long)c);
 }
 
 }  // namespace dfr

@@ -7,8 +7,7 @@
 namespace dfr {
 
 // TimeStepDiffDFSPH::beginStep (TimeStepDiffDFSPH.cpp:353-430)
-__global__ void k_begin_step(const Params *Pp, StepState *st, BodyDev *bodies) {
-  const Params &P = *Pp;
+__global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, BodyDev *bodies) {
   const int b = threadIdx.x;
   if (b == 0) {
     st->step_count += 1;
@@ -278,8 +277,7 @@ __device__ inline void mgr_position_rotation_chain(const Params &P, BodyDev *bod
 // End of TimeStepDiffDFSPH::step (time advance :645, backwardPerStep :493-524, endStep :432-490) followed by
 // the rest of SimulatorBase::timeStepNoGUI (:1159-1169): manager stages, BoundarySimulator::updateBoundaryForces
 // (BoundarySimulator.cpp:10-36), RigidBody3dBoundarySimulator::velocityTimeStep / positionTimeStep (:278-344).
-__global__ void k_body_update(const Params *Pp, StepState *st, BodyDev *bodies, MgrBlock *M) {
-  const Params &P = *Pp;
+__global__ void k_body_update(const __grid_constant__ Params P, StepState *st, BodyDev *bodies, MgrBlock *M) {
   const double h = st->h;  // NEW h: backwardPerStep, the manager and the rigid integrator re-read the TimeManager
   const int b = threadIdx.x;
   if (b == 0) {

@@ -102,12 +102,13 @@ struct MgrBlock {
   m33 f_v0, f_w0, t_v0, t_w0;
 };
 
-// Warp-interleaved neighbour list: the k-th neighbour of sorted particle i sits at
-// idx[woff[i >> 5] + k * 32 + (i & 31)], so that a warp reads 128 contiguous bytes per k.
+// Warp-interleaved ELL neighbour list: the k-th neighbour of sorted particle i sits at
+// idx[((i >> 5) * cap + k) * 32 + (i & 31)], so that a warp reads 128 contiguous bytes per k.
 struct NbrList {
   const int *cnt;
-  const unsigned int *woff;
   const int *idx;
+  int cap;
 };
+__device__ __forceinline__ const int *nbr_row(const NbrList &l, int i) { return l.idx + ((size_t)(i >> 5) * l.cap) * 32 + (i & 31); }
 
 }  // namespace dfr
