@@ -63,7 +63,11 @@ class Config(C.Structure):
         ("target_time", C.c_double),
         ("uniform_acc_rb_time", C.c_double),
         ("max_emitted_particles", C.c_int32),
-        ("reserved_i", C.c_int32 * 7),
+        ("neighbor_capacity_fluid", C.c_int32),
+        ("neighbor_capacity_boundary", C.c_int32),
+        ("body_neighbor_capacity", C.c_int32),
+        ("grid_reach", C.c_int32),
+        ("reserved_i", C.c_int32 * 3),
         ("reserved_d", C.c_double * 8),
     ]
 

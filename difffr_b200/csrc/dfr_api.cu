@@ -434,8 +434,8 @@ int launch_step(dfr_context *c) {
   }
   if (c->cfg.surface_tension_method == 2)
     LAUNCH(c, k_normals, g, 128, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
-  LAUNCH(c, k_nonpressure, g, 128, c->P, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
-         c->density.p, c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
+  LAUNCH(c, k_nonpressure, g, 128, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+         c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
   c->vcur = 1 - c->vcur;
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
   LAUNCH(c, k_cfl_finish, 1, 32, c->P, c->dSt.p);
@@ -748,9 +748,10 @@ int dfr_finalize(dfr_context *c) {
   }
   for (int64_t i = 0; i < c->nf0; i++) grow(c->h_fx[3 * i], c->h_fx[3 * i + 1], c->h_fx[3 * i + 2]);
   if (c->nf0 == 0 && c->n_b == 0) return fail(c, DFR_ERR_INVALID, "empty scene");
-  // ---- grid: cell edge slightly above the support radius, two cells of margin, capped cell count ----
-  double cell = hs * (1.0 + 1.0e-7);
-  const double margin = 2.0;
+  // ---- grid: cell edge slightly above (support radius / reach), margin cells, capped cell count ----
+  int reach = c->cfg.grid_reach > 0 ? c->cfg.grid_reach : 2;
+  double cell = hs * (1.0 + 1.0e-7) / reach;
+  double margin = 2.0 * reach;
   for (;;) {
     double nx = std::floor((hi[0] - lo[0]) / cell) + 1 + 2 * margin;
     double ny = std::floor((hi[1] - lo[1]) / cell) + 1 + 2 * margin;
@@ -759,8 +760,14 @@ int dfr_finalize(dfr_context *c) {
       P.grid.nx = (int)nx; P.grid.ny = (int)ny; P.grid.nz = (int)nz;
       break;
     }
-    cell *= 1.26;
+    if (reach > 1) {  // fall back to support-radius cells before growing them
+      reach = 1;
+      cell = hs * (1.0 + 1.0e-7);
+      margin = 2.0;
+    } else
+      cell *= 1.26;
   }
+  P.grid.reach = reach;
   P.grid.ox = lo[0] - margin * cell; P.grid.oy = lo[1] - margin * cell; P.grid.oz = lo[2] - margin * cell;
   P.grid.inv_cell = 1.0 / cell;
   P.grid.ncells = P.grid.nx * P.grid.ny * P.grid.nz;
@@ -792,9 +799,9 @@ int dfr_finalize(dfr_context *c) {
   CU(c->cnt_f.alloc(N)); CU(c->cnt_b.alloc(N));
   // ELL capacities: neighbours per particle (support 4r, spacing 2r: ~30 at rest, more under compression).  Slots
   // beyond a row's count are never touched, so generous capacities cost address space, not bandwidth.
-  c->cap_f = cfg.reserved_i[0] > 0 ? cfg.reserved_i[0] : 96;
-  c->cap_b = cfg.reserved_i[1] > 0 ? cfg.reserved_i[1] : 64;
-  const int per_d = cfg.reserved_i[2] > 0 ? cfg.reserved_i[2] : 96;
+  c->cap_f = ((cfg.neighbor_capacity_fluid > 0 ? cfg.neighbor_capacity_fluid : 96) + 3) & ~3;
+  c->cap_b = ((cfg.neighbor_capacity_boundary > 0 ? cfg.neighbor_capacity_boundary : 64) + 3) & ~3;
+  const int per_d = cfg.body_neighbor_capacity > 0 ? cfg.body_neighbor_capacity : 96;
   c->cap_d = (unsigned int)(ND * per_d);
   const size_t nwarp = (N + 31) / 32;
   CU(c->idx_f.alloc(nwarp * 32 * (size_t)c->cap_f)); CU(c->idx_b.alloc(nwarp * 32 * (size_t)c->cap_b));
@@ -1185,7 +1192,7 @@ int dfr_get_neighbors(dfr_context *c, int set_a, int set_b, int32_t *counts, int
       for (int i = 0; i < n; i++) {
         std::vector<int32_t> &r = rows[ids[i]];
         for (int k = 0; k < cnt[i]; k++) {
-          const int j = idx[((size_t)(i >> 5) * cap + (size_t)k) * 32 + (i & 31)];
+          const int j = idx[((((size_t)(i >> 5) * (cap >> 2) + (size_t)(k >> 2)) * 32 + (size_t)(i & 31)) << 2) + (size_t)(k & 3)];
           if (fluid)
             r.push_back(ids[j]);
           else {

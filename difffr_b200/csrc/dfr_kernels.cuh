@@ -9,6 +9,12 @@
 namespace dfr {
 
 #define DFR_EPS 1.0e-5  // m_eps, TimeStepDiffDFSPH.h:26
+struct Rec2 {
+  double4 a, b;
+};
+struct Rec3 {
+  double4 a, b, c;
+};
 #define DFR_FULL 0xffffffffu
 
 // read-only 32-byte record load as ONE 256-bit instruction (sm_100: LDG.E.ENL2.256.CONSTANT).  A gathered
@@ -363,9 +369,10 @@ template <class F>
 __device__ __forceinline__ void for_each_in_range(const Params &P, const GridView &g, double px, double py, double pz, int self, F f) {
   int cx, cy, cz;
   cell_of(P.grid, px, py, pz, cx, cy, cz);
-  const int xlo = max(cx - 1, 0), xhi = min(cx + 1, P.grid.nx - 1);
-  for (int z = max(cz - 1, 0); z <= min(cz + 1, P.grid.nz - 1); z++)
-    for (int y = max(cy - 1, 0); y <= min(cy + 1, P.grid.ny - 1); y++) {
+  const int R = P.grid.reach;
+  const int xlo = max(cx - R, 0), xhi = min(cx + R, P.grid.nx - 1);
+  for (int z = max(cz - R, 0); z <= min(cz + R, P.grid.nz - 1); z++)
+    for (int y = max(cy - R, 0); y <= min(cy + R, P.grid.ny - 1); y++) {
       const int s = (int)g.cell_start[cell_lin(P.grid, xlo, y, z)];
       const int e = (int)g.cell_start[cell_lin(P.grid, xhi, y, z) + 1];
       for (int p = s; p < e; p++) {
@@ -378,8 +385,7 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
 }
 
 // Single scan: fluid->fluid and fluid->boundary neighbour lists in a warp-interleaved ELL layout
-// (slot k of sorted particle i at idx[((i >> 5) * cap + k) * 32 + (i & 31)]: a warp reads 128 contiguous
-// bytes per k, and no count pass / prefix sum is needed).  Rows longer than cap raise error_flags; the
+// (dfr_types.cuh: "ELL-4"; no count pass / prefix sum is needed).  Rows longer than cap raise error_flags; the
 // host then grows the capacity and replays the step (dfr_api.cu: launch_step).
 __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
                                                     GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
@@ -390,18 +396,17 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
   if (i < n) {
     const int lane = i & 31;
     const double4 p = pos[i];
-    int *of = idx_f + ((size_t)(i >> 5) * cap_f) * 32 + lane;
-    int *ob = idx_b + ((size_t)(i >> 5) * cap_b) * 32 + lane;
+    (void)lane;
     for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int j) {
-      if (cf < cap_f) of[(size_t)cf * 32] = j;
+      if (cf < cap_f) idx_f[nbr_slot(cap_f, i, cf)] = j;
       cf++;
     });
     if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int j) {
-      if (cb < cap_b) ob[(size_t)cb * 32] = j;
+      if (cb < cap_b) idx_b[nbr_slot(cap_b, i, cb)] = j;
       cb++;
     });
     if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int j) {
-      if (cb < cap_b) ob[(size_t)cb * 32] = j;
+      if (cb < cap_b) idx_b[nbr_slot(cap_b, i, cb)] = j;
       cb++;
     });
     if (cf > cap_f) atomicOr(&st->error_flags, 1);
@@ -484,34 +489,26 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
   double dens = P.volume * P.W_zero;
   double S = 0.0;
   d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij
-  {
-    const int n = lf.cnt[i];
-    const int *o = nbr_row(lf, i);
-    for (int k = 0; k < n; k++) {
-      const int j = o[(size_t)k * 32];
-      const double4 pj = ldg4(pos + j);
-      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-      double c;
-      const double wv = cubic_W_and_grad(P, dot(r, r), c);
-      dens += P.volume * wv;
-      const d3 g = (P.volume * c) * r;
-      S += dot(g, g);
-      G += g;
-    }
-  }
-  {
-    const int n = lb.cnt[i];
-    const int *o = nbr_row(lb, i);
-    for (int k = 0; k < n; k++) {
-      const int j = o[(size_t)k * 32];
-      const double4 pj = ldg4(bpos + j);
-      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-      double c;
-      const double wv = cubic_W_and_grad(P, dot(r, r), c);
-      dens += pj.w * wv;
-      G += (pj.w * c) * r;
-    }
-  }
+  for_neighbors4(
+      lf, i, i, [&](int j) { return ldg4(pos + j); },
+      [&](const double4 &pj, int) {
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        double c;
+        const double wv = cubic_W_and_grad(P, dot(r, r), c);
+        dens += P.volume * wv;
+        const d3 g = (P.volume * c) * r;
+        S += dot(g, g);
+        G += g;
+      });
+  for_neighbors4(
+      lb, i, 0, [&](int j) { return ldg4(bpos + j); },
+      [&](const double4 &pj, int) {
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        double c;
+        const double wv = cubic_W_and_grad(P, dot(r, r), c);
+        dens += pj.w * wv;
+        G += (pj.w * c) * r;
+      });
   density[i] = dens * P.density0;
   // (x, rho) record: k_normals gathers position and density of a neighbour in one 256-bit load
   stg4(xrho + i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
@@ -543,29 +540,21 @@ __global__ void __launch_bounds__(128) k_rho(const __grid_constant__ Params P, S
     const double4 vi = vel[i];
       double delta = 0.0;
     const int nF = lf.cnt[i];
-    {
-      const int *o = nbr_row(lf, i);
-      for (int k = 0; k < nF; k++) {
-        const int j = o[(size_t)k * 32];
-        const double4 pj = ldg4(pos + j);
-        const double4 vj = ldg4(vel + j);
-        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double c = cubic_grad_coeff(P, dot(r, r));
-        delta += (P.volume * c) * ((vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z);
-      }
-    }
+    for_neighbors4(
+        lf, i, i, [&](int j) { return Rec2{ldg4(pos + j), ldg4(vel + j)}; },
+        [&](const Rec2 &q, int) {
+          const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
+          const double c = cubic_grad_coeff(P, dot(r, r));
+          delta += (P.volume * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
+        });
     const int nB = lb.cnt[i];
-    {
-      const int *o = nbr_row(lb, i);
-      for (int k = 0; k < nB; k++) {
-        const int j = o[(size_t)k * 32];
-        const double4 pj = ldg4(bpos + j);
-        const double4 vj = ldg4(bvel + j);
-        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double c = cubic_grad_coeff(P, dot(r, r));
-        delta += (pj.w * c) * ((vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z);
-      }
-    }
+    for_neighbors4(
+        lb, i, 0, [&](int j) { return Rec2{ldg4(bpos + j), ldg4(bvel + j)}; },
+        [&](const Rec2 &q, int) {
+          const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
+          const double c = cubic_grad_coeff(P, dot(r, r));
+          delta += (q.a.w * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
+        });
     double rho;
     if (PRESSURE) {
       rho = fmax(density[i] / P.density0 + h * delta, 1.0);
@@ -664,32 +653,25 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
   if (ITER && accumulate_kappa) kappa[i] += ki;
   double4 v = vel[i];
   d3 dv = mk3(0, 0, 0);
-  {
-    const int n = lf.cnt[i];
-    const int *o = nbr_row(lf, i);
-    for (int k = 0; k < n; k++) {
-      const int j = o[(size_t)k * 32];
-      const double4 pj = ldg4(xk + j);
-      const double kSum = ki + pj.w;
-      if (fabs(kSum) > DFR_EPS) {
-        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double c = cubic_grad_coeff(P, dot(r, r));
-        // vel -= h * kSum * (-V gradW)
-        dv += (h * kSum * P.volume * c) * r;
-      }
-    }
-  }
-  if (fabs(ki) > DFR_EPS) {
-    const int n = lb.cnt[i];
-    const int *o = nbr_row(lb, i);
-    for (int k = 0; k < n; k++) {
-      const int j = o[(size_t)k * 32];
-      const double4 pj = ldg4(bpos + j);
-      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-      const double c = cubic_grad_coeff(P, dot(r, r));
-      dv += (h * ki * pj.w * c) * r;
-    }
-  }
+  for_neighbors4(
+      lf, i, i, [&](int j) { return ldg4(xk + j); },
+      [&](const double4 &pj, int) {
+        const double kSum = ki + pj.w;
+        if (fabs(kSum) > DFR_EPS) {
+          const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+          const double c = cubic_grad_coeff(P, dot(r, r));
+          // vel -= h * kSum * (-V gradW)
+          dv += (h * kSum * P.volume * c) * r;
+        }
+      });
+  if (fabs(ki) > DFR_EPS)
+    for_neighbors4(
+        lb, i, 0, [&](int j) { return ldg4(bpos + j); },
+        [&](const double4 &pj, int) {
+          const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+          const double c = cubic_grad_coeff(P, dot(r, r));
+          dv += (h * ki * pj.w * c) * r;
+        });
   v.x += dv.x;
   v.y += dv.y;
   v.z += dv.z;
@@ -908,21 +890,19 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
   if (i >= st->nf) return;
   const double4 pi = xrho[i];
   d3 n = mk3(0, 0, 0);
-  const int cnt = lf.cnt[i];
-  const int *o = nbr_row(lf, i);
-  for (int k = 0; k < cnt; k++) {
-    const int j = o[(size_t)k * 32];
-    const double4 pj = ldg4(xrho + j);
-    const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-    const double c = cubic_grad_coeff(P, dot(r, r));
-    n += (P.mass / pj.w * c) * r;
-  }
+  for_neighbors4(
+      lf, i, i, [&](int j) { return ldg4(xrho + j); },
+      [&](const double4 &pj, int) {
+        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double c = cubic_grad_coeff(P, dot(r, r));
+        n += (P.mass / pj.w * c) * r;
+      });
   // w carries the particle's density so that the force pass gathers (n_j, rho_j) in one record
   stg4(normal + i, make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, pi.w));
 }
 
-__global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
-                                                      const double4 *bvel, NbrList lf, NbrList lb, const double *density,
+__global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
+                                                      const double4 *bvel, NbrList lf, NbrList lb,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
                                                       double4 *acc_out, double4 *vel_out) {
   const int nf = st->nf;
@@ -930,10 +910,10 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
   const double h = st->h_step;
   double mag = 0.0;
   if (i < nf) {
-    const double4 pi = pos[i];
+    const double4 pi = xrho[i];
     const double4 vi = vel[i];
-      d3 a = mk3(P.gx, P.gy, P.gz);
-    const double rhoi = density[i];
+    d3 a = mk3(P.gx, P.gy, P.gz);
+    const double rhoi = pi.w;
     const bool st_on = (P.st_method == 2);
     const bool visc_on = (P.visc_method == 1);
     d3 ni = mk3(0, 0, 0);
@@ -942,52 +922,50 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
       ni = mk3(n4.x, n4.y, n4.z);
     }
     const double h2s = P.support_radius * P.support_radius;
-    {
-      const int cnt = lf.cnt[i];
-      const int *o = nbr_row(lf, i);
-      for (int k = 0; k < cnt; k++) {
-        const int j = o[(size_t)k * 32];
-        const double4 pj = ldg4(pos + j);
-        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double r2 = dot(r, r);
-        double rhoj;
-        if (st_on) {
-          const double4 nj = ldg4(normal + j);
-          rhoj = nj.w;
-          const double K_ij = 2.0 * P.density0 / (rhoi + rhoj);
-          d3 accel = mk3(0, 0, 0);
-          if (r2 > 1.0e-9) accel -= (P.surface_tension * P.mass * cohesion_W(P, r2) * rsqrt(r2)) * r;
-          accel -= P.surface_tension * mk3(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z);
-          a += K_ij * accel;
-        } else
-          rhoj = __ldg(density + j);
-        if (visc_on) {
-          const double4 vj = ldg4(vel + j);
-          const double c = cubic_grad_coeff(P, r2);
-          const double vx = (vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z;
-          a += (10.0 * P.viscosity * (P.mass / rhoj) * vx / (r2 + 0.01 * h2s) * c) * r;
-        }
-      }
-    }
+    // (x_j, rho_j) comes as one record (xrho); the normal and the velocity are gathered only when their
+    // force is switched on
+    for_neighbors4<2>(
+        lf, i, i,
+        [&](int j) {
+          Rec3 q;
+          q.a = ldg4(xrho + j);
+          if (st_on) q.b = ldg4(normal + j);
+          if (visc_on) q.c = ldg4(vel + j);
+          return q;
+        },
+        [&](const Rec3 &q, int) {
+          const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
+          const double r2 = dot(r, r);
+          const double rhoj = q.a.w;
+          if (st_on) {
+            const double K_ij = 2.0 * P.density0 / (rhoi + rhoj);
+            d3 accel = mk3(0, 0, 0);
+            if (r2 > 1.0e-9) accel -= (P.surface_tension * P.mass * cohesion_W(P, r2) * rsqrt(r2)) * r;
+            accel -= P.surface_tension * mk3(ni.x - q.b.x, ni.y - q.b.y, ni.z - q.b.z);
+            a += K_ij * accel;
+          }
+          if (visc_on) {
+            const double c = cubic_grad_coeff(P, r2);
+            const double vx = (vi.x - q.c.x) * r.x + (vi.y - q.c.y) * r.y + (vi.z - q.c.z) * r.z;
+            a += (10.0 * P.viscosity * (P.mass / rhoj) * vx / (r2 + 0.01 * h2s) * c) * r;
+          }
+        });
     if ((st_on && P.surface_tension_b != 0.0) || (visc_on && P.viscosity_b != 0.0)) {
       // boundary adhesion / boundary viscosity: zero coefficients in every shipped scene; the
       // reaction force of the boundary-viscosity term on dynamic bodies is not carried here.
-      const int cnt = lb.cnt[i];
-      const int *o = nbr_row(lb, i);
-      for (int k = 0; k < cnt; k++) {
-        const int j = o[(size_t)k * 32];
-        const double4 pj = ldg4(bpos + j);
-        const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double r2 = dot(r, r);
-        if (st_on && P.surface_tension_b != 0.0 && r2 > 1.0e-9)
-          a -= (P.surface_tension_b * P.density0 * pj.w * adhesion_W(P, r2) * rsqrt(r2)) * r;
-        if (visc_on && P.viscosity_b != 0.0) {
-          const double4 vj = ldg4(bvel + j);
-          const double c = cubic_grad_coeff(P, r2);
-          const double vx = (vi.x - vj.x) * r.x + (vi.y - vj.y) * r.y + (vi.z - vj.z) * r.z;
-          a += (10.0 * P.viscosity_b * (P.density0 * pj.w / rhoi) * vx / (r2 + 0.01 * h2s) * c) * r;
-        }
-      }
+      for_neighbors4(
+          lb, i, 0, [&](int j) { return Rec2{ldg4(bpos + j), ldg4(bvel + j)}; },
+          [&](const Rec2 &q, int) {
+            const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
+            const double r2 = dot(r, r);
+            if (st_on && P.surface_tension_b != 0.0 && r2 > 1.0e-9)
+              a -= (P.surface_tension_b * P.density0 * q.a.w * adhesion_W(P, r2) * rsqrt(r2)) * r;
+            if (visc_on && P.viscosity_b != 0.0) {
+              const double c = cubic_grad_coeff(P, r2);
+              const double vx = (vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z;
+              a += (10.0 * P.viscosity_b * (P.density0 * q.a.w / rhoi) * vx / (r2 + 0.01 * h2s) * c) * r;
+            }
+          });
     }
     acc_out[i] = make_double4(a.x, a.y, a.z, 0.0);
     const d3 vn = mk3(vi.x + h * a.x, vi.y + h * a.y, vi.z + h * a.z);

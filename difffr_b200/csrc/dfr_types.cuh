@@ -7,13 +7,15 @@
 namespace dfr {
 
 // Uniform cell grid shared by all point sets (fluid, static boundary, dynamic boundary).
-// Cell edge >= support radius; coordinates are clamped into the grid, which keeps the 27-cell
-// stencil exhaustive for particles that leave the initial bounding box.
+// Cell edge >= support radius / reach (reach = 2: half-size cells and a 5x5x5 stencil, 15.6 h^3 of candidates
+// instead of 27 h^3, and a finer sort order); coordinates are clamped into the grid, which keeps the stencil
+// exhaustive for particles that leave the initial bounding box.
 struct GridGeom {
   double ox, oy, oz;
   double inv_cell;
   int nx, ny, nz;
   int ncells;
+  int reach;
 };
 
 // Solver parameters that never change during a trajectory (constant for all kernels).
@@ -102,13 +104,48 @@ struct MgrBlock {
   m33 f_v0, f_w0, t_v0, t_w0;
 };
 
-// Warp-interleaved ELL neighbour list: the k-th neighbour of sorted particle i sits at
-// idx[((i >> 5) * cap + k) * 32 + (i & 31)], so that a warp reads 128 contiguous bytes per k.
+// Warp-interleaved ELL neighbour list in groups of four slots ("ELL-4"): slots 4g..4g+3 of sorted particle i are
+// one int4 at ((int4 *)idx)[((i >> 5) * (cap / 4) + g) * 32 + (i & 31)].  A warp reads 512 contiguous bytes per
+// group with one LDG.128 per lane, and every loop over neighbours naturally works on batches of four: the four
+// record gathers of a batch are issued back to back before any of them is consumed (memory-level parallelism;
+// profiles/r1b showed the gathers latency-bound with one or two loads in flight per warp).
 struct NbrList {
   const int *cnt;
   const int *idx;
-  int cap;
+  int cap;  // slots per particle, multiple of 4
 };
-__device__ __forceinline__ const int *nbr_row(const NbrList &l, int i) { return l.idx + ((size_t)(i >> 5) * l.cap) * 32 + (i & 31); }
+__device__ __forceinline__ size_t nbr_slot(int cap, int i, int k) {
+  return ((((size_t)(i >> 5) * (size_t)(cap >> 2) + (size_t)(k >> 2)) * 32 + (size_t)(i & 31)) << 2) + (size_t)(k & 3);
+}
+// load(j) -> payload gathered for neighbour j; use(payload, j) accumulates it.  Neighbours are consumed in slot
+// order, so sums have the same order as a plain sequential loop.  Slots past the row's count are replaced by the
+// always-valid index `safe` for the (discarded) gather.
+template <int U = 4, class Load, class Use>
+__device__ __forceinline__ void for_neighbors4(const NbrList &l, int i, int safe, Load load, Use use) {
+  static_assert(U == 1 || U == 2 || U == 4, "sub-batch of the int4 group");
+  const int n = l.cnt[i];
+  if (n <= 0) return;
+  const int4 *row = reinterpret_cast<const int4 *>(l.idx) + ((size_t)(i >> 5) * (size_t)(l.cap >> 2)) * 32 + (i & 31);
+  const int nb = (n + 3) >> 2;
+  int4 jn = __ldg(row);
+  for (int b = 0; b < nb; b++) {
+    const int4 j4 = jn;
+    if (b + 1 < nb) jn = __ldg(row + (size_t)(b + 1) * 32);
+    const int k0 = b << 2;
+    int j[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+    for (int u = 1; u < 4; u++)
+      if (k0 + u >= n) j[u] = safe;
+#pragma unroll
+    for (int s = 0; s < 4; s += U) {  // U gathers in flight per record array (register budget of 2-/3-record kernels)
+      decltype(load(0)) p[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) p[u] = load(j[s + u]);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (k0 + s + u < n) use(p[u], j[s + u]);
+    }
+  }
+}
 
 }  // namespace dfr

@@ -80,7 +80,12 @@ typedef struct dfr_config {
   double target_time;              /* "targetTime" */
   double uniform_acc_rb_time;      /* "uniformAccelerateRBTime" */
   int32_t max_emitted_particles;   /* capacity reserved for emitters (Emitter.cpp) */
-  int32_t reserved_i[7];
+  /* Device-side tuning (0 = default).  These have no counterpart in the reference; they never change results. */
+  int32_t neighbor_capacity_fluid;    /* fluid neighbours stored per fluid particle (default 96) */
+  int32_t neighbor_capacity_boundary; /* boundary neighbours stored per fluid particle (default 64) */
+  int32_t body_neighbor_capacity;     /* mean fluid neighbours stored per dynamic boundary particle (default 96) */
+  int32_t grid_reach;                 /* cell edge = support radius / grid_reach, stencil (2 reach + 1)^3 (default 2) */
+  int32_t reserved_i[3];
   double reserved_d[8];
 } dfr_config;
 

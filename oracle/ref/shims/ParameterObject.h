@@ -212,6 +212,20 @@ class ParameterObject {
     return (int)m_parameters.size() - 1;
   }
 
+  // convenience setters by parameter id (used as setGroup(ID, "...") throughout the reference)
+  void setGroup(const unsigned int id, const std::string &s) { getParameter(id)->setGroup(s); }
+  void setDescription(const unsigned int id, const std::string &s) { getParameter(id)->setDescription(s); }
+  void setHotKey(const unsigned int id, const std::string &s) { getParameter(id)->setHotKey(s); }
+  void setReadOnly(const unsigned int id, bool b) { getParameter(id)->setReadOnly(b); }
+  void setVisible(const unsigned int id, bool b) { getParameter(id)->setVisible(b); }
+  void setName(const unsigned int id, const std::string &s) { getParameter(id)->setName(s); }
+  void setLabel(const unsigned int id, const std::string &s) { getParameter(id)->setLabel(s); }
+  std::string getName(const unsigned int id) const { return getParameter(id)->getName(); }
+  std::string getLabel(const unsigned int id) const { return getParameter(id)->getLabel(); }
+  std::string getGroup(const unsigned int id) const { return getParameter(id)->getGroup(); }
+  std::string getDescription(const unsigned int id) const { return getParameter(id)->getDescription(); }
+  ParameterBase::DataTypes getType(const unsigned int id) const { return getParameter(id)->getType(); }
+
   template <typename T> T getValue(const unsigned int id) const { return static_cast<Parameter<T> *>(getParameter(id))->getValue(); }
   template <typename T> void setValue(const unsigned int id, const T v) { static_cast<Parameter<T> *>(getParameter(id))->setValue(v); }
   template <typename T> T *getVecValue(const unsigned int id) const { return static_cast<VectorParameter<T> *>(getParameter(id))->getValue(); }
