@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdfr.so")
+LIB_PATH = os.environ.get("DFR_LIBRARY") or os.path.join(_HERE, "csrc", "libdfr.so")  # DFR_LIBRARY: tuning builds
 
 
 class DfrError(RuntimeError):

@@ -9,6 +9,22 @@
 namespace dfr {
 
 #define DFR_EPS 1.0e-5  // m_eps, TimeStepDiffDFSPH.h:26
+// gathers in flight per record array and neighbour batch (tuned on B200, see profiles/)
+#ifndef DFR_RHO_U
+#define DFR_RHO_U 1
+#endif
+#ifndef DFR_PUSH_U
+#define DFR_PUSH_U 2
+#endif
+#ifndef DFR_NP_U
+#define DFR_NP_U 2
+#endif
+#ifndef DFR_DF_U
+#define DFR_DF_U 4
+#endif
+#ifndef DFR_RHO_BLOCKS
+#define DFR_RHO_BLOCKS 8
+#endif
 struct Rec2 {
   double4 a, b;
 };
@@ -489,7 +505,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
   double dens = P.volume * P.W_zero;
   double S = 0.0;
   d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij
-  for_neighbors4(
+  for_neighbors4<DFR_DF_U>(
       lf, i, i, [&](int j) { return ldg4(pos + j); },
       [&](const double4 &pj, int) {
         const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
@@ -525,7 +541,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
 enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
 
 template <bool PRESSURE, int MODE>
-__global__ void __launch_bounds__(128) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
                                               const int *state, double *kappa, double *dadv, double4 *xk, double *partials) {
   if (MODE == RHO_ITER) {
@@ -540,7 +556,7 @@ __global__ void __launch_bounds__(128) k_rho(const __grid_constant__ Params P, S
     const double4 vi = vel[i];
       double delta = 0.0;
     const int nF = lf.cnt[i];
-    for_neighbors4(
+    for_neighbors4<DFR_RHO_U>(
         lf, i, i, [&](int j) { return Rec2{ldg4(pos + j), ldg4(vel + j)}; },
         [&](const Rec2 &q, int) {
           const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
@@ -548,7 +564,7 @@ __global__ void __launch_bounds__(128) k_rho(const __grid_constant__ Params P, S
           delta += (P.volume * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
         });
     const int nB = lb.cnt[i];
-    for_neighbors4(
+    for_neighbors4<DFR_RHO_U>(
         lb, i, 0, [&](int j) { return Rec2{ldg4(bpos + j), ldg4(bvel + j)}; },
         [&](const Rec2 &q, int) {
           const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
@@ -653,7 +669,7 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
   if (ITER && accumulate_kappa) kappa[i] += ki;
   double4 v = vel[i];
   d3 dv = mk3(0, 0, 0);
-  for_neighbors4(
+  for_neighbors4<DFR_PUSH_U>(
       lf, i, i, [&](int j) { return ldg4(xk + j); },
       [&](const double4 &pj, int) {
         const double kSum = ki + pj.w;
@@ -924,7 +940,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
     const double h2s = P.support_radius * P.support_radius;
     // (x_j, rho_j) comes as one record (xrho); the normal and the velocity are gathered only when their
     // force is switched on
-    for_neighbors4<2>(
+    for_neighbors4<DFR_NP_U>(
         lf, i, i,
         [&](int j) {
           Rec3 q;
