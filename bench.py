@@ -124,33 +124,52 @@ def make_scene(n_particles):
 
 
 # ------------------------------------------------------------------------------------------------
+class quiet_stdout:
+    """The reference's own code prints to stdout (e.g. Dynamic3dRigidBody::determineMassProperties); bench.py must
+    print exactly one JSON line, so fd 1 is parked on /dev/null while the CPU arm runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 def cpu_arm(lib_path, prefix, scene, steps, warmup):
     """Time the CPU implementation (oracle port or oracle/_ref) on `scene`; returns (particle-steps/s, cores, ms/step, info)."""
     from difffr_b200 import scenes
     from difffr_b200.cabi import Context
 
-    lib = ctypes.CDLL(lib_path)
-    ctx = scenes.build_context(lambda **k: Context(lib=lib, prefix=prefix, **k), scene, **CFG)
-    cores = 1
-    if hasattr(lib, prefix + "num_threads"):
-        f = getattr(lib, prefix + "num_threads")
-        f.restype = ctypes.c_int
-        cores = int(f())
-    if warmup:
-        ctx.step(warmup)
-    p0 = ctx.step_info().total_particle_steps
-    t0 = time.perf_counter()
-    ctx.step(steps)
-    dt = time.perf_counter() - t0
-    info = ctx.step_info()
-    psteps = info.total_particle_steps - p0
+    with quiet_stdout():
+        lib = ctypes.CDLL(lib_path)
+        ctx = scenes.build_context(lambda **k: Context(lib=lib, prefix=prefix, **k), scene, **CFG)
+        cores = 1
+        if hasattr(lib, prefix + "num_threads"):
+            f = getattr(lib, prefix + "num_threads")
+            f.restype = ctypes.c_int
+            cores = int(f())
+        if warmup:
+            ctx.step(warmup)
+        p0 = ctx.step_info().total_particle_steps
+        t0 = time.perf_counter()
+        ctx.step(steps)
+        dt = time.perf_counter() - t0
+        info = ctx.step_info()
+        psteps = info.total_particle_steps - p0
+        ctx.close()
     return psteps / dt, cores, 1e3 * dt / max(steps, 1), info
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "fast", "libref.so")
     fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
     if os.path.exists(ref_so):
         lib_path, prefix, kind = ref_so, "ref_", "reference"
@@ -343,7 +362,7 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline:
         fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
-        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "fast", "libref.so")
         if os.path.exists(ref_so):
             lib_path, prefix, kind = ref_so, "ref_", "reference"
         else:

@@ -1,0 +1,54 @@
+"""The CPU oracle (the restatement in oracle/dfsph_oracle.cpp) against golden vectors recorded from the reference's
+own code (tests/golden/make_golden.py -> oracle/_ref/libref.so).  This is what pins the oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import golden_util
+from conftest import ROOT, rel_err
+
+
+@pytest.mark.parametrize("name", golden_util.CASES)
+def test_oracle_reproduces_reference_golden_vectors(oracle_factory, name):
+    worst = golden_util.replay_and_compare(oracle_factory, name, state_tol=1e-9, grad_tol=1e-9)
+    assert worst <= 1e-9  # observed <= ~1e-13: identical algorithm, only summation order differs
+
+
+def test_golden_files_present():
+    assert len(golden_util.CASES) >= 4
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref.so")), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_against_live_reference_build():
+    """Fresh random scene through the reference's own translation units (only where oracle/_ref was built).
+    Runs in a subprocess: the reference keeps its state in process-wide singletons."""
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes, sys, numpy as np
+sys.path.insert(0, %r)
+from difffr_b200 import scenes
+from difffr_b200.cabi import Context
+olib = ctypes.CDLL(%r); rlib = ctypes.CDLL(%r)
+sc = scenes.dam_break_scene(2200, n_boxes=2, jitter=0.25, seed=23)
+kw = dict(surface_tension_method=2, surface_tension=0.3, max_error=0.05, target_time=0.05, use_rigid_gradient_manager=1)
+o = scenes.build_context(lambda **k: Context(lib=olib, prefix="orc_", **k), sc, **kw)
+r = scenes.build_context(lambda **k: Context(lib=rlib, prefix="ref_", **k), sc, **kw)
+def rel(a, b): return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+worst = 0.0
+for s in range(5):
+    o.step(1); r.step(1)
+    assert o.step_info().iterations == r.step_info().iterations
+    for f in ("position", "velocity", "density", "kappa", "kappa_v"): worst = max(worst, rel(o.fluid(f), r.fluid(f)))
+    for b in (1, 2):
+        so, sr = o.body_state(b), r.body_state(b)
+        for k in so: worst = max(worst, rel(so[k], sr[k]))
+        for w in range(16): worst = max(worst, rel(o.manager_grad(b, b, w), r.manager_grad(b, b, w)))
+print("WORST", worst)
+assert worst < 1e-9
+''' % (ROOT, os.path.join(ROOT, "oracle", "liboracle.so"), os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
