@@ -68,6 +68,8 @@ struct dfr_context {
   std::vector<double> h_fx, h_fv;
   int64_t nf0 = 0, nf_cap = 0;
   std::vector<HostBody> bodies;
+  std::vector<EmitterDev> h_emitters;
+  DevBuf<EmitterDev> dEmitters;
   int n_static_p = 0, n_dyn_p = 0, n_b = 0, dyn_begin = 0;
   bool has_emitters = false;
 
@@ -443,6 +445,14 @@ int launch_step(dfr_context *c) {
   if (rc) return rc;
   LAUNCH(c, k_advect_x, g, 128, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->pstate[a].p, c->kappa[a].p,
          c->cfg.use_pressure_warmstart ? 1 : 0);
+  if (!c->h_emitters.empty()) {  // emitParticles (TimeStepDiffDFSPH.cpp:637-641)
+    LAUNCH(c, k_emit_release, g, 128, c->dSt.p, c->pstate[a].p);
+    for (int ei = 0; ei < (int)c->h_emitters.size(); ei++) {
+      LAUNCH(c, k_emit_animate, g, 128, c->P, c->dSt.p, c->dEmitters.p, ei, c->pos[a].p, c->vel[c->vcur].p, c->pstate[a].p);
+      LAUNCH(c, k_emit_spawn, 1, 256, c->P, c->dSt.p, c->dEmitters.p, ei, (int)c->nf_cap, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p,
+             c->kappav[a].p, c->pid[a].p, c->pstate[a].p);
+    }
+  }
   if (c->P.n_bodies > 0) {
     LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
     LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p);
@@ -494,6 +504,8 @@ int reset_device_state(dfr_context *c) {
     CU(cudaStreamSynchronize(c->stream));
     if (c->acc_rows.n) CU(cudaMemsetAsync(c->acc_rows.p, 0, c->acc_rows.n * sizeof(double), c->stream));
   }
+  if (!c->h_emitters.empty())  // Emitter::reset: next emit time back to the start
+    CU(cudaMemcpyAsync(c->dEmitters.p, c->h_emitters.data(), c->h_emitters.size() * sizeof(EmitterDev), cudaMemcpyHostToDevice, c->stream));
   StepState st;
   std::memset(&st, 0, sizeof(st));
   st.h = c->cfg.time_step_size;
@@ -593,7 +605,7 @@ void dfr_destroy(dfr_context *c) {
   c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
-  c->off_d.free(); c->dSt.free();
+  c->off_d.free(); c->dSt.free(); c->dEmitters.free();
   for (auto &p : c->prof_pending) {
     cudaEventDestroy(p.e0);
     cudaEventDestroy(p.e1);
@@ -655,8 +667,24 @@ int dfr_set_init_v_omega(dfr_context *c, int body, const double v0[3], const dou
   return DFR_OK;
 }
 
-int dfr_add_emitter(dfr_context *c, int, int, const double *, const double *, double, double, double) {
-  return fail(c, DFR_ERR_INVALID, "emitters are not implemented in the CUDA path yet");
+int dfr_add_emitter(dfr_context *c, int width, int height, const double position[3], const double rot[9], double velocity,
+                    double emit_start, double emit_end) {
+  if (!c) return DFR_ERR_INVALID;
+  if (c->finalized) return fail(c, DFR_ERR_STATE, "add_emitter after finalize");
+  if (width <= 0 || height <= 0 || !position || !rot || !(velocity > 0.0)) return fail(c, DFR_ERR_INVALID, "bad emitter");
+  EmitterDev e;
+  std::memset(&e, 0, sizeof(e));
+  e.width = width;
+  e.height = height;
+  e.x = mk3(position[0], position[1], position[2]);
+  for (int k = 0; k < 9; k++) e.rot.a[k] = rot[k];
+  e.velocity = velocity;
+  e.emit_start = emit_start;
+  e.emit_end = emit_end;
+  e.next_emit_time = emit_start;
+  e.emit_counter = 0;
+  c->h_emitters.push_back(e);
+  return DFR_OK;
 }
 
 int dfr_finalize(dfr_context *c) {
@@ -775,7 +803,8 @@ int dfr_finalize(dfr_context *c) {
   // ---- allocations ----
   c->nf_cap = c->nf0 + std::max(0, cfg.max_emitted_particles);
   const size_t N = (size_t)std::max<int64_t>(c->nf_cap, 1);
-  c->launch_nf = (int)c->nf0;
+  c->launch_nf = c->h_emitters.empty() ? (int)c->nf0 : (int)c->nf_cap;  // emitters grow st->nf on the device
+  CU(c->dEmitters.alloc(std::max<size_t>(c->h_emitters.size(), 1)));
   const int nc = P.grid.ncells;
   CU(c->dSt.alloc(1));
   for (int k = 0; k < 2; k++) {

@@ -548,6 +548,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
   const int nf = st->nf;
+  if ((int)(blockIdx.x * blockDim.x) >= nf) return;  // grids are sized for the emitter capacity; only live blocks take a ticket
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double h = PRESSURE ? st->h : st->h_step;
   double err = 0.0;
@@ -1058,6 +1059,84 @@ __global__ void k_advect_x(const StepState *st, double4 *pos, const double4 *vel
     pos[i] = p;
   }
   if (scale_kappa) kappa[i] *= st->h * st->h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Emitter: EmitterSystem::step (EmitterSystem.cpp:54-83) and Emitter::emitParticles (Emitter.cpp:89-227), box
+// emitter without particle reuse.  Runs after x += h v and before the time advance (TimeStepDiffDFSPH.cpp:637-645).
+// ---------------------------------------------------------------------------------------------
+// particles animated by an emitter in the previous step become Active again (EmitterSystem.cpp:64-76)
+__global__ void k_emit_release(const StepState *st, int *state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < st->nf && state[i] == 1) state[i] = 0;
+}
+__device__ __forceinline__ d3 emitter_velocity(const Params &P, const EmitterDev &e, double t) {
+  const d3 dir = mk3(e.rot.a[0], e.rot.a[3], e.rot.a[6]);  // first column of the rotation
+  if (t < e.emit_start || t > e.emit_end) return (P.particle_radius * 10.0 * (1.0 / 0.25)) * dir;  // Emitter.cpp:112-113
+  return e.velocity * dir;
+}
+// particles inside the emitter box move with the emit velocity (Emitter.cpp:116-140)
+__global__ void k_emit_animate(const __grid_constant__ Params P, const StepState *st, const EmitterDev *emitters, int ei, double4 *pos,
+                               double4 *vel, int *state) {
+  const EmitterDev &e = emitters[ei];
+  const double t = st->time;
+  if (!(t >= e.emit_start - 0.25 && t <= e.emit_end)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  const d3 dir = mk3(e.rot.a[0], e.rot.a[3], e.rot.a[6]);
+  const d3 ev = emitter_velocity(P, e, t);
+  const double diam = 2.0 * P.particle_radius;
+  const d3 half = mk3(0.5 * (2.0 * P.support_radius), 0.5 * (e.height * diam + 2.0 * diam), 0.5 * (e.width * diam + 2.0 * diam));
+  const d3 c0 = e.x + (0.5 * P.support_radius) * dir;
+  double4 p = pos[i];
+  const d3 xl = transpose(e.rot) * (mk3(p.x, p.y, p.z) - c0);
+  if (fabs(xl.x) < half.x && fabs(xl.y) < half.y && fabs(xl.z) < half.z) {
+    const double h = st->h;
+    vel[i] = make_double4(ev.x, ev.y, ev.z, 0.0);
+    p.x += h * ev.x;
+    p.y += h * ev.y;
+    p.z += h * ev.z;
+    pos[i] = p;
+    state[i] = 1;
+  }
+}
+// appends width x height particles when the emit time has come (Emitter.cpp:142-227); one block
+__global__ void k_emit_spawn(const __grid_constant__ Params P, StepState *st, EmitterDev *emitters, int ei, int capacity, double4 *pos,
+                             double4 *vel, double *kappa, double *kappav, int *pid, int *state) {
+  EmitterDev &e = emitters[ei];
+  const double t = st->time;
+  if (t < e.next_emit_time || t > e.emit_end) return;
+  const int nf = st->nf;
+  const double diam = 2.0 * P.particle_radius;
+  const d3 ev = emitter_velocity(P, e, t);
+  const d3 axisH = mk3(e.rot.a[1], e.rot.a[4], e.rot.a[7]);
+  const d3 axisW = mk3(e.rot.a[2], e.rot.a[5], e.rot.a[8]);
+  const double startX = -0.5 * (e.width - 1) * diam;
+  const double startZ = -0.5 * (e.height - 1) * diam;
+  const double dt = t - e.next_emit_time + st->h;
+  const d3 offset = e.x + dt * ev;
+  if (nf < capacity) {
+    const int total = e.width * e.height;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+      const int i = k / e.height, j = k % e.height;
+      const int index = nf + k;
+      if (index < capacity) {
+        const d3 x = (i * diam + startX) * axisW + (j * diam + startZ) * axisH + offset;
+        pos[index] = make_double4(x.x, x.y, x.z, 0.0);
+        vel[index] = make_double4(ev.x, ev.y, ev.z, 0.0);
+        state[index] = 1;
+        kappa[index] = 0.0;  // SimulationDataDiffDFSPH::emittedParticles (:173-183)
+        kappav[index] = 0.0;
+        pid[index] = index;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (nf < capacity) st->nf = min(nf + e.width * e.height, capacity);
+    e.next_emit_time += diam / e.velocity;
+    e.emit_counter += 1;
+  }
 }
 
 }  // namespace dfr

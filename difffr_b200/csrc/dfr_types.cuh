@@ -95,6 +95,16 @@ struct BodyDev {
   m43 q_v0, q_w0, partial_q_w;
 };
 
+// Box emitter (Emitter.cpp:40-87, 89-227; type 0), state advanced on the device
+struct EmitterDev {
+  int width, height;
+  d3 x;
+  m33 rot;
+  double velocity, emit_start, emit_end;
+  double next_emit_time;
+  int emit_counter;
+};
+
 // RigidBodyGradientManager block (R, RR)  (RigidBodyGradientManager.h:62-91)
 struct MgrBlock {
   m33 xn_v0, xn_w0, vn_v0, vn_w0, wn_v0, wn_w0;

@@ -223,3 +223,42 @@ def test_medium_scene_parity_50k(gpu_factory, oracle_factory):
         gpu.step(1)
         orc.step(1)
         compare_step(gpu, orc, sc)
+
+
+def test_emitter_grows_the_fluid(gpu_factory, oracle_factory):
+    """Box emitter (Emitter.cpp:89-227, config 4 of BASELINE.json): emitted particles, AnimatedByEmitter state and the
+    particle count agree step by step."""
+    sc = scenes.dam_break_scene(2000, n_boxes=1)
+    he = sc["tank_half_extent"]
+    rot = np.array([0, 1, 0, -1, 0, 0, 0, 0, 1], dtype=np.float64)  # emit direction (first column) = -y
+    sc["emitters"] = [dict(width=4, height=3, position=(0.3 * he[0], 1.2 * he[1], 0.0), rotation=rot, velocity=2.0, emit_start=0.0, emit_end=0.03),
+                      dict(width=2, height=2, position=(0.6 * he[0], 1.1 * he[1], 0.1), rotation=rot, velocity=3.0, emit_start=0.004, emit_end=0.02)]
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=200, cfl_max_time_step=0.002, target_time=1.0)
+    n0 = gpu.num_fluid
+    for s in range(30):
+        gpu.step(1)
+        orc.step(1)
+        assert gpu.num_fluid == orc.num_fluid, s
+        compare_step(gpu, orc, sc, state_tol=1e-6)
+    assert gpu.num_fluid > n0
+    gpu.reset()
+    orc.reset()
+    assert gpu.num_fluid == n0 == orc.num_fluid
+    gpu.step(12)
+    orc.step(12)
+    compare_step(gpu, orc, sc)
+
+
+def test_emitter_capacity_is_respected(gpu_factory, oracle_factory):
+    sc = scenes.dam_break_scene(1500, n_boxes=0)
+    he = sc["tank_half_extent"]
+    rot = np.array([0, 1, 0, -1, 0, 0, 0, 0, 1], dtype=np.float64)
+    sc["emitters"] = [dict(width=3, height=3, position=(0.3 * he[0], 1.2 * he[1], 0.0), rotation=rot, velocity=4.0, emit_start=0.0, emit_end=1.0)]
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=20, cfl_max_time_step=0.002, target_time=1.0)
+    n0 = gpu.num_fluid
+    for s in range(40):
+        gpu.step(1)
+        orc.step(1)
+        assert gpu.num_fluid == orc.num_fluid <= n0 + 20
+    assert gpu.num_fluid == n0 + 20
+    compare_step(gpu, orc, sc)
