@@ -1053,9 +1053,9 @@ __global__ void k_advect_x(const StepState *st, double4 *pos, const double4 *vel
     const double h = st->h_step;
     double4 p = pos[i];
     const double4 v = vel[i];
-    p.x += h * v.x;
-    p.y += h * v.y;
-    p.z += h * v.z;
+    p.x = __dadd_rn(p.x, __dmul_rn(h, v.x));  // mul + add like the reference's x86 code, not an FMA (see k_emit_animate)
+    p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
+    p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
     pos[i] = p;
   }
   if (scale_kappa) kappa[i] *= st->h * st->h;
@@ -1093,9 +1093,11 @@ __global__ void k_emit_animate(const __grid_constant__ Params P, const StepState
   if (fabs(xl.x) < half.x && fabs(xl.y) < half.y && fabs(xl.z) < half.z) {
     const double h = st->h;
     vel[i] = make_double4(ev.x, ev.y, ev.z, 0.0);
-    p.x += h * ev.x;
-    p.y += h * ev.y;
-    p.z += h * ev.z;
+    // no FMA contraction: emitted sheets sit on an exact 2r lattice (pairs at distance == support radius), so their
+    // positions have to be the bits the reference's mul + add produces
+    p.x = __dadd_rn(p.x, __dmul_rn(h, ev.x));
+    p.y = __dadd_rn(p.y, __dmul_rn(h, ev.y));
+    p.z = __dadd_rn(p.z, __dmul_rn(h, ev.z));
     pos[i] = p;
     state[i] = 1;
   }

@@ -233,7 +233,12 @@ def test_emitter_grows_the_fluid(gpu_factory, oracle_factory):
     rot = np.array([0, 1, 0, -1, 0, 0, 0, 0, 1], dtype=np.float64)  # emit direction (first column) = -y
     sc["emitters"] = [dict(width=4, height=3, position=(0.3 * he[0], 1.2 * he[1], 0.0), rotation=rot, velocity=2.0, emit_start=0.0, emit_end=0.03),
                       dict(width=2, height=2, position=(0.6 * he[0], 1.1 * he[1], 0.1), rotation=rot, velocity=3.0, emit_start=0.004, emit_end=0.02)]
-    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=200, cfl_max_time_step=0.002, target_time=1.0)
+    # Surface tension is off here on purpose: emitted sheets form an exact 2r lattice whose in-sheet / sheet-to-sheet
+    # pairs sit at distance == support radius.  Akinci-2013's normal term -k (n_i - n_j) is not kernel-weighted
+    # (SurfaceTension_Akinci2013.cpp:104-110), so whether such a pair is in the list changes the force by O(1): a
+    # discontinuity of the reference algorithm itself once released particles differ in the last bit.
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=200, cfl_max_time_step=0.002, target_time=1.0,
+                          surface_tension_method=0)
     n0 = gpu.num_fluid
     for s in range(30):
         gpu.step(1)
@@ -254,7 +259,8 @@ def test_emitter_capacity_is_respected(gpu_factory, oracle_factory):
     he = sc["tank_half_extent"]
     rot = np.array([0, 1, 0, -1, 0, 0, 0, 0, 1], dtype=np.float64)
     sc["emitters"] = [dict(width=3, height=3, position=(0.3 * he[0], 1.2 * he[1], 0.0), rotation=rot, velocity=4.0, emit_start=0.0, emit_end=1.0)]
-    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=20, cfl_max_time_step=0.002, target_time=1.0)
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=20, cfl_max_time_step=0.002, target_time=1.0,
+                          surface_tension_method=0)
     n0 = gpu.num_fluid
     for s in range(40):
         gpu.step(1)
