@@ -95,7 +95,7 @@ SYMBOLS = [
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
     "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
-    "set_profiling", "get_kernel_profile",
+    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode",
 ]
 
 GRAD_NAMES = [
@@ -209,6 +209,8 @@ class Context:
         proto("get_neighbors", C.c_int, vp, C.c_int, C.c_int, ip, ip, i64, C.POINTER(i64))
         proto("add_emitter", C.c_int, vp, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double)
         proto("get_device_time_ms", C.c_int, vp, dp, C.POINTER(i64))
+        proto("reset_gradient", C.c_int, vp)
+        proto("set_gradient_mode", C.c_int, vp, C.c_int)
         if hasattr(L, p + "set_profiling"):  # the CPU oracle has no kernels to profile
             proto("set_profiling", C.c_int, vp, C.c_int)
             proto("get_kernel_profile", C.c_int, vp, C.c_int, C.c_char_p, C.c_int, dp, C.POINTER(i64))
@@ -268,6 +270,12 @@ class Context:
     # -- stepping -------------------------------------------------------------------------
     def reset(self):
         self._check(self._fn("reset")(self._ctx))
+
+    def reset_gradient(self):
+        self._check(self._fn("reset_gradient")(self._ctx))
+
+    def set_gradient_mode(self, mode):
+        self._check(self._fn("set_gradient_mode")(self._ctx, int(mode)))
 
     def step(self, n=1):
         self._check(self._fn("step")(self._ctx, int(n)))

@@ -932,6 +932,25 @@ int dfr_reset(dfr_context *c) {
   return reset_device_state(c);
 }
 
+int dfr_reset_gradient(dfr_context *c) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  cudaSetDevice(c->device);
+  if (c->P.n_bodies > 0) {
+    LAUNCH(c, k_reset_gradient, 1, 32, c->P, c->dBodies.p);
+    if (c->acc_rows.n) CU(cudaMemsetAsync(c->acc_rows.p, 0, c->acc_rows.n * sizeof(double), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return DFR_OK;
+}
+
+int dfr_set_gradient_mode(dfr_context *c, int mode) {
+  if (!c) return DFR_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(c, DFR_ERR_INVALID, "gradient mode must be 0 (Complete), 1 (Incomplete) or 2 (RigidGradOnly)");
+  c->cfg.gradient_mode = mode;
+  c->P.gradient_mode = mode;  // Params travel by value with every launch (__grid_constant__)
+  return DFR_OK;
+}
+
 int dfr_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);

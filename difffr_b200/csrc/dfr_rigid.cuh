@@ -35,6 +35,22 @@ __global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, Bo
   }
 }
 
+// BoundaryModel_Akinci2012::reset_gradient (BoundaryModel_Akinci2012.cpp:62-108), non-articulated branch
+__global__ void k_reset_gradient(const __grid_constant__ Params P, BodyDev *bodies) {
+  const int b = threadIdx.x;
+  if (b >= P.n_bodies) return;
+  BodyDev &B = bodies[b];
+  if (!B.dynamic) return;
+  B.net_f_v = B.net_f_x = B.net_f_w = B.net_t_v = B.net_t_x = B.net_t_w = m33::zero();
+  B.net_f_q = B.net_t_q = m34::zero();
+  B.v_v0 = m33::identity();
+  B.v_w0 = m33::zero();
+  B.w_w0 = m33::identity();
+  B.w_v0 = m33::zero();
+  B.q_w0 = B.q_v0 = B.partial_q_w = m43::zero();
+  B.x_v0 = B.x_w0 = m33::zero();
+}
+
 // sums the accumulator rows of each body in block order (deterministic) and clears them
 // (replaces accumulate_and_reset_gradient, BoundaryModel_Akinci2012.cpp:453-497, and the per-thread
 // force slots of BoundaryModel.cpp:38-54)

@@ -128,6 +128,16 @@ int dfr_load_fluid_state(dfr_context *ctx, const double *x, const double *v,
 /* SimulatorBase::reset (SimulatorBase.cpp:887-934). */
 int dfr_reset(dfr_context *ctx);
 
+/* TimeStepDiffDFSPH::reset_gradient -> BoundaryModel_Akinci2012::reset_gradient for every dynamic body
+ * (TimeStepDiffDFSPH.cpp:2234-2240, BoundaryModel_Akinci2012.cpp:62-108): the sensitivities restart from
+ * d(v,omega)/d(v0,omega0) = I, everything else zero, at the current state (short-horizon restarts,
+ * cartpole-diff-controller.py:228).  As in the reference, the RigidBodyGradientManager blocks are left alone. */
+int dfr_reset_gradient(dfr_context *ctx);
+
+/* Simulation::setGradientMode (SimulationModule.cpp:206; Simulation.h:173): 0 Complete, 1 Incomplete,
+ * 2 RigidGradOnly.  Legal at any time between steps. */
+int dfr_set_gradient_mode(dfr_context *ctx, int mode);
+
 /* n x SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169): TimeStepDiffDFSPH::step,
  * gradient-manager stages, rigid velocity/position update.  No host round trip inside. */
 int dfr_step(dfr_context *ctx, int n_steps);

@@ -1706,6 +1706,20 @@ int orc_reset(dfr_context *c) {  // SimulatorBase::reset (SimulatorBase.cpp:887-
   return DFR_OK;
 }
 
+int orc_reset_gradient(dfr_context *c) {  // TimeStepDiffDFSPH::reset_gradient (TimeStepDiffDFSPH.cpp:2234-2240)
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  for (auto &b : c->bodies)
+    if (b.dynamic) b.resetGradient();  // BoundaryModel_Akinci2012::reset_gradient (:62-108) zeroes/identities the same members
+  return DFR_OK;
+}
+
+int orc_set_gradient_mode(dfr_context *c, int mode) {  // Simulation::setGradientMode (Simulation.h:173)
+  if (!c) return DFR_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(c, DFR_ERR_INVALID, "gradient mode must be 0, 1 or 2");
+  c->cfg.gradient_mode = mode;
+  return DFR_OK;
+}
+
 int orc_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   const auto t0 = std::chrono::steady_clock::now();

@@ -481,6 +481,19 @@ static void one_step(dfr_context *c) {  // SimulatorBase::timeStepNoGUI (:1142-1
   c->total_psteps += sim->getFluidModel(0)->numActiveParticles();
 }
 
+int ref_reset_gradient(dfr_context *c) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  ts()->reset_gradient();  // TimeStepDiffDFSPH.cpp:2234-2240
+  return DFR_OK;
+}
+
+int ref_set_gradient_mode(dfr_context *c, int mode) {
+  if (!c) return DFR_ERR_INVALID;
+  Simulation::getCurrent()->setGradientMode(mode);
+  c->cfg.gradient_mode = mode;
+  return DFR_OK;
+}
+
 int ref_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   const auto t0 = std::chrono::steady_clock::now();

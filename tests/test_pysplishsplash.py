@@ -1,0 +1,90 @@
+"""Host logic of the pybind11 `pysplishsplash` module (no GPU): the surface the reference's optimisation scripts use
+ is present under the reference's names, the scene loader follows SceneLoader / createFluidBlocks, and the
+module refuses to run without a CUDA device instead of falling back to a CPU path."""
+import numpy as np
+import pytest
+
+from pysph_util import import_sph, write_scene
+
+
+def test_surface_names_match_the_reference_bindings():
+    sph = import_sph()
+    need = {
+        sph.Exec.SimulatorBase: ["init", "setGui", "initSimulation", "initSimulationWithDeferredInit", "runSimulation", "runNewTrajectory",
+                                 "forwardFixedSteps", "singleTimeStep", "timeStepNoGUI", "reset", "cleanup", "setTimeStepCB",
+                                 "setTimeStepCallBefore", "setResetCB", "saveState", "loadState", "loadStateWithRigidExisted",
+                                 "setStateExportPath", "getOutputPath", "getBoundarySimulator", "getRigidBodyGradientManager",
+                                 "setValueBool", "setValueInt", "setValueFloat", "getValueBool", "getValueInt", "getValueFloat",
+                                 "STATE_EXPORT", "STATE_EXPORT_FPS", "PAUSE", "STOP_AT"],
+        sph.Simulation: ["getCurrent", "getTimeStep", "getBoundaryModel", "setGradientMode", "getGradientMode", "useRigidGradientManager",
+                         "numberOfBoundaryModels"],
+        sph.TimeStepDiffDFSPH: ["get_boundary_model", "get_loss", "set_loss", "get_loss_x", "set_loss_x", "get_loss_rotation",
+                                "set_loss_rotation", "set_init_v_rb", "set_init_omega_rb", "set_init_omega_rb_to_joint", "get_init_v_rb",
+                                "get_init_omega_rb", "get_target_x", "set_target_x", "get_target_angle_in_radian",
+                                "get_target_quaternion_vec4", "is_trajectory_finish_callback", "clear_all_callbacks",
+                                "is_in_new_trajectory", "get_step_count", "add_log", "set_custom_log_message", "get_custom_log_message",
+                                "reset_gradient", "get_num_1ring_fluid_particle"],
+        sph.BoundaryModelAkinci2012: ["get_position_rb", "get_quaternion_rb_vec4", "get_velocity_rb", "get_angular_velocity_rb",
+                                      "set_velocity_rb", "set_angular_velocity_rb", "get_grad_x_to_v0", "get_grad_x_to_omega0",
+                                      "get_grad_quaternion_to_v0", "get_grad_quaternion_to_omega0", "get_grad_v_to_v0",
+                                      "get_grad_v_to_omega0", "get_grad_omega_to_v0", "get_grad_omega_to_omega0", "getForce", "getTorque",
+                                      "getRigidBodyObject", "numberOfParticles", "getPosition", "getVelocity", "getVolume"],
+        sph.Exec.RigidBodyGradientManager: ["reset", "get_grad_x_to_v0", "get_grad_x_to_omega0", "get_grad_q_to_v0", "get_grad_q_to_omega0",
+                                            "get_grad_net_force_to_vn", "get_grad_net_torque_to_omega_n"],
+        sph.RigidBodyObject: ["getPosition", "getVelocity", "getAngularVelocity", "getRotation", "setVelocity", "setAngularVelocity",
+                              "getMass", "isDynamic"],
+        sph.TimeManager: ["getCurrent", "getTime", "getTimeStepSize"],
+        sph.GUI: ["Simulator_GUI_imgui"],
+        sph.Utilities.Timing: ["printAverageTimes", "printTimeSums"],
+    }
+    missing = [(k.__name__, n) for k, names in need.items() for n in names if not hasattr(k, n)]
+    assert not missing, missing
+
+
+def test_scene_loader_follows_the_reference_schema(tmp_path):
+    sph = import_sph()
+    path = write_scene(tmp_path, target_time=0.3)
+    d = sph._load_scene_summary(path)
+    # createFluidBlocks (SimulatorBase.cpp:1638-1735): steps = round(extent / 2r) - 1 per axis
+    r = 0.025
+    steps = [int(round(e / (2 * r))) - 1 for e in (0.6, 0.35, 0.6)]
+    assert d["num_fluid"] == steps[0] * steps[1] * steps[2]
+    assert d["particle_radius"] == r and d["target_time"] == 0.3
+    assert d["surface_tension_method"] == 2 and d["surface_tension"] == 0.2
+    assert [b["dynamic"] for b in d["bodies"]] == [False, True]
+    assert d["bodies"][1]["density"] == 500
+    np.testing.assert_allclose(d["bodies"][1]["init_v"], [0.5, -0.2, 0.1])
+    np.testing.assert_allclose(d["bodies"][1]["init_omega"], [0.3, 1.0, -0.4])
+    np.testing.assert_allclose(d["bodies"][1]["target_x"], [0.2, 0.3, 0.0])
+    # surface sampling density: ~ area / (1.35 r)^2 within 25 %
+    area = 2 * (1.0 * 0.8 + 0.8 * 0.6 + 1.0 * 0.6)
+    n = d["bodies"][0]["num_particles"]
+    assert 0.75 < n * (1.35 * r) ** 2 / area < 1.25, n
+    # --param override in the reference's syntax (SimulatorBase.cpp:734-839)
+    d2 = sph._load_scene_summary(path, "Fluid:surfaceTension:0.35,maxError:0.01")
+    assert d2["surface_tension"] == 0.35 and d2["max_error"] == 0.01
+    with pytest.raises(RuntimeError):
+        sph._load_scene_summary(path, "noSuchParameter:1")
+
+
+def test_scene_loader_rejects_what_is_outside_the_path(tmp_path):
+    sph = import_sph()
+    with pytest.raises(RuntimeError, match="simulationMethod"):
+        sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"simulationMethod": 1}))
+    with pytest.raises(RuntimeError, match="boundaryHandlingMethod"):
+        sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"boundaryHandlingMethod": 2}))
+    with pytest.raises(RuntimeError):
+        sph._load_scene_summary(str(tmp_path / "missing.json"))
+
+
+def test_no_cpu_fallback(tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sph = import_sph()
+    base = sph.Exec.SimulatorBase()
+    base.init(sceneFile=write_scene(tmp_path), useGui=False, outputDir=str(tmp_path / "out"), stopAt=1.0)
+    with pytest.raises(sph.DfrError, match="no CUDA device"):
+        base.initSimulation()
+    assert not sph.Simulation.hasCurrent()

@@ -1,0 +1,126 @@
+"""The pybind11 `pysplishsplash` module on the GPU: the call sequence of the reference's gradient-based-optimize.py
+(init -> initSimulation -> setGradientMode -> setTimeStepCB -> runSimulation, reset() inside the callback) reproduces what
+the C ABI gives when driven directly, and the CPU oracle on the same scene."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from pysph_util import import_sph, write_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def run_script_like(sph, scene_path, out_dir, n_iterations=2, gradient_mode=1):
+    """Same structure as experiments/rigid_body_trajectory_optimization/python/gradient-based-optimize.py:386-528."""
+    base = sph.Exec.SimulatorBase()
+    base.init(sceneFile=scene_path, useGui=False, initialPause=False, useCache=False, stopAt=100.0, stateFile="", outputDir=out_dir)
+    gui = sph.GUI.Simulator_GUI_imgui(base)
+    base.setGui(gui)
+    base.initSimulation()
+    sim = sph.Simulation.getCurrent()
+    timestep = sim.getTimeStep()
+    sim.setGradientMode(gradient_mode)
+    assert sim.getGradientMode() == gradient_mode
+    records = []
+
+    def time_step_callback():
+        if not timestep.is_trajectory_finish_callback():
+            return
+        bm = timestep.get_boundary_model(1)
+        rec = dict(
+            x=bm.get_position_rb(), q=bm.get_quaternion_rb_vec4(), v=bm.get_velocity_rb(), w=bm.get_angular_velocity_rb(),
+            gx_v=bm.get_grad_x_to_v0(), gx_w=bm.get_grad_x_to_omega0(), gq_v=bm.get_grad_quaternion_to_v0(),
+            gq_w=bm.get_grad_quaternion_to_omega0(), steps=timestep.get_step_count(), t=sph.TimeManager.getCurrent().getTime(),
+        )
+        records.append(rec)
+        timestep.set_loss(float(np.sum((rec["x"] - timestep.get_target_x(1)) ** 2)))
+        timestep.add_log(f"iteration {len(records)} loss {timestep.get_loss()}")
+        base.reset()  # legal inside the callback (gradient-based-optimize.py:475)
+        timestep.clear_all_callbacks()
+        if len(records) >= n_iterations:
+            base.stop()
+
+    base.setTimeStepCB(time_step_callback)
+    base.runSimulation()
+    base.cleanup()
+    return records
+
+
+def test_script_flow_reproduces_itself_and_the_oracle(tmp_path, oracle_factory):
+    sph = import_sph()
+    path = write_scene(tmp_path, target_time=0.02)
+    recs = run_script_like(sph, path, str(tmp_path / "out"))
+    assert len(recs) == 2
+    a, b = recs
+    assert a["steps"] == b["steps"] and a["steps"] > 3
+    for k in ("x", "q", "v", "w", "gx_v", "gx_w", "gq_v", "gq_w"):
+        assert np.array_equal(a[k], b[k]), k  # reset() restores the snapshot bit for bit; the CUDA path is deterministic
+    assert a["gx_v"].shape == (3, 3) and a["gq_w"].shape == (4, 3) and a["q"].shape == (4,)
+    assert np.abs(a["gx_v"]).max() > 0
+    assert (tmp_path / "out" / "log" / "SPH_log.txt").read_text().count("iteration") == 2
+
+    # the same scene through the CPU oracle (checker only): body samples are taken from the module itself
+    base = sph.Exec.SimulatorBase()
+    base.init(sceneFile=path, useGui=False, outputDir=str(tmp_path / "out2"), stopAt=100.0)
+    base.initSimulationWithDeferredInit()
+    sim = sph.Simulation.getCurrent()
+    ts = sim.getTimeStep()
+    orc = oracle_factory(particle_radius=0.025, surface_tension_method=2, surface_tension=0.2, target_time=0.02, max_error=0.05,
+                         max_error_v=0.1, cfl_max_time_step=0.005, uniform_acc_rb_time=0.0)
+    r = 0.025
+    steps = [int(round(e / (2 * r))) - 1 for e in (0.6, 0.35, 0.6)]
+    j, k, l = np.meshgrid(*[np.arange(s) for s in steps], indexing="ij")
+    fluid = np.stack([j.ravel(), k.ravel(), l.ravel()], axis=1) * (2 * r) + (np.array([-0.5, 0.0, -0.3]) + 2 * r)
+    orc.set_fluid(fluid)
+    for i in range(sim.numberOfBoundaryModels()):
+        bm = sim.getBoundaryModel(i)
+        n = bm.numberOfParticles()
+        x0 = np.array([bm.getPosition0(p) for p in range(n)])
+        rb = bm.getRigidBodyObject()
+        q = rb.getRotation()  # (x, y, z, w) like Eigen coeffs()
+        orc.add_body(x0, rb.isDynamic(), 500.0 if rb.isDynamic() else 1000.0, rb.getPosition(), [q[3], q[0], q[1], q[2]])
+    orc.set_init_v_omega(1, ts.get_init_v_rb(1), ts.get_init_omega_rb(1))
+    orc.finalize()
+    n_orc = orc.run_trajectory(10000)
+    assert n_orc == a["steps"]
+    so = orc.body_state(1)
+    assert rel_err(a["x"], so["x"]) < 1e-6 and rel_err(a["q"], so["q"]) < 1e-6
+    assert rel_err(a["v"], so["v"]) < 1e-6 and rel_err(a["w"], so["omega"]) < 1e-6
+    assert rel_err(a["gx_v"], orc.body_grad(1, 0)) < 1e-4 and rel_err(a["gx_w"], orc.body_grad(1, 1)) < 1e-4
+    assert rel_err(a["gq_v"], orc.body_grad(1, 2)) < 1e-4 and rel_err(a["gq_w"], orc.body_grad(1, 3)) < 1e-4
+    base.cleanup()
+
+
+def test_new_init_velocity_changes_the_trajectory_and_state_files_round_trip(tmp_path):
+    sph = import_sph()
+    path = write_scene(tmp_path, target_time=0.01)
+    base = sph.Exec.SimulatorBase()
+    base.init(sceneFile=path, useGui=False, outputDir=str(tmp_path / "o"), stopAt=100.0)
+    base.initSimulationWithDeferredInit()
+    ts = sph.Simulation.getCurrent().getTimeStep()
+    bm = ts.get_boundary_model(1)
+    base.runNewTrajectory()
+    x_a = bm.get_position_rb()
+    n_a = ts.get_step_count()
+    ts.set_init_v_rb(1, np.array([1.5, -0.2, 0.1]))
+    np.testing.assert_allclose(ts.get_init_v_rb(1), [1.5, -0.2, 0.1])
+    base.runNewTrajectory()
+    x_b = bm.get_position_rb()
+    assert x_b[0] - x_a[0] > 0.5 * (1.5 - 0.5) * 0.01  # the body travelled further in x
+    # finite-difference check of d x / d v0 against the propagated sensitivity (first column)
+    gx = bm.get_grad_x_to_v0()
+    fd = (x_b - x_a) / 1.0
+    assert np.linalg.norm(fd - gx[:, 0]) < 0.25 * np.linalg.norm(gx[:, 0])
+    # state file round trip: save after the trajectory, perturb by running on, load -> fluid state restored as snapshot
+    sfile = base.saveState(str(tmp_path / "state"))
+    t_saved = sph.TimeManager.getCurrent().getTime()
+    assert sfile.endswith(".dfrs") and t_saved > 0
+    base.forwardFixedSteps(2)
+    base.loadState(sfile)  # re-bases the simulation on the stored fluid state (time restarts, as reset + checkLoadState)
+    assert sph.TimeManager.getCurrent().getTime() == 0.0
+    base.forwardFixedSteps(1)
+    assert ts.get_step_count() == 1 and n_a > 1
+    # reset_gradient restarts the sensitivities at the current state (TimeStepDiffDFSPH.cpp:2234-2240)
+    ts.reset_gradient()
+    assert np.array_equal(bm.get_grad_v_to_v0(), np.eye(3)) and not bm.get_grad_x_to_v0().any()
+    base.cleanup()
