@@ -140,3 +140,37 @@ def build_context(ctx_factory, scene, **cfg_overrides):
             ctx.set_init_v_omega(i, b.get("init_v", (0, 0, 0)), b.get("init_omega", (0, 0, 0)))
     ctx.finalize()
     return ctx
+
+
+def contact_scene(n_target=1500, radius=0.025, jitter=0.0, seed=0):
+    """Two dynamic boxes within the contact range of the tank floor and of each other, in a shallow pool.
+
+    Feeds the penalty rigid-rigid contact solver (BASELINE.json configs[2], `useRigidContactSolver`): a boundary
+    particle is "in contact" as soon as a particle of another body lies within the support radius (4 r), and the
+    penalty force acts while its artificial density exceeds the rest value (RigidContactSolver.cpp:307-345, 479-486).
+    Box 1 sits 2 r above the floor, box 2 leans against box 1 (gap 2 r), both tilted so that many particles have
+    distinct contact depths; both get initial linear and angular velocities so that the Coulomb friction term and
+    the gyroscopic increment of every contacting particle are exercised.
+    """
+    sc = dam_break_scene(n_target, n_boxes=0, radius=radius, jitter=jitter, seed=seed)
+    d = 2 * radius
+    he = np.array([5 * radius] * 3)
+    # irregular samples, like the reference's Poisson-disk ones: on a symmetric lattice the contact normal
+    # x_r - sum(x_k w)/sum(w) of a face-centre particle is exactly zero and the reference's friction Jacobian divides by
+    # |normal force| = 0 (RigidContactSolver.cpp:505) -> NaN on both sides
+    rng_b = np.random.default_rng(1234 + seed)
+    samples = box_surface_samples(he, d)
+    samples = samples + rng_b.uniform(-0.3 * radius, 0.3 * radius, size=samples.shape)
+    floor_y = 0.0
+    x0 = -sc["tank_half_extent"][0] + 0.5 * (0.4 * 2 * sc["tank_half_extent"][0])
+    pos1 = np.array([x0, floor_y + he[1] + 2.2 * radius, -1.5 * he[2]])
+    pos2 = pos1 + np.array([0.0, 0.6 * radius, 2 * he[2] + 2.0 * radius])
+    sc["bodies"].append(dict(x_local=samples, dynamic=True, density=1500.0, position=pos1, quat=quat_from_axis_angle([0.2, 1.0, 0.1], 0.05),
+                             init_v=(0.4, -0.3, 0.2), init_omega=(1.5, -2.0, 0.7)))
+    sc["bodies"].append(dict(x_local=samples, dynamic=True, density=800.0, position=pos2, quat=quat_from_axis_angle([1.0, 0.3, -0.2], 0.08),
+                             init_v=(-0.2, -0.1, -0.5), init_omega=(-1.0, 0.5, 2.0)))
+    keep = np.ones(len(sc["fluid"]), dtype=bool)
+    for bd in sc["bodies"][1:]:
+        keep &= ~np.all(np.abs(sc["fluid"] - bd["position"]) < he + d, axis=1)
+    sc["fluid"] = np.ascontiguousarray(sc["fluid"][keep])
+    return sc

@@ -293,6 +293,11 @@ struct Body {
   Mat43 grad_q_to_v0, grad_q_to_omega0, partial_grad_qn_to_omega_n;
   // SimulationDataDiffDFSPH per-body
   Vec3 init_v, init_omega;
+  // RigidContactSolver per-particle state (RigidContactSolver.h:134-147), id order
+  std::vector<double> c_vol0, c_density0, c_density, c_vol, c_vel;
+  // storage order of the reference (slot -> particle id): CompactNSearch z_sort permutes dynamic point sets
+  // (BoundaryModel_Akinci2012.cpp:388-416); only the penalty solver's per-contact addTorque sequence depends on it
+  std::vector<int32_t> order;
   // neighbour lists
   NList nb_fluid;                 // body particle -> fluid
   std::vector<NList> nb_body;     // body particle -> other body particles (boundary volume / contact)
@@ -430,8 +435,11 @@ struct dfr_context {
   int64_t totalIter = 0, totalIterV = 0, totalParticleSteps = 0, totalNeighbors = 0;
   double cpu_ms = 0.0;
 
-  // contact solver state (RigidContactSolver)
-  // (filled by oracle_contact.inc when enabled)
+  // contact solver state (RigidContactSolver), see oracle_contact.inc
+  Kernels Kc;                                       // kernel with the contact support radius (W_with_h)
+  std::vector<std::pair<int, int32_t>> in_contact;  // m_particle_indices_in_contact
+  int64_t sortCounter = 0;                          // TimeStepDiffDFSPH::m_counter (z-sort every 500 steps)
+  int64_t numContacts = 0;
 };
 
 namespace {
@@ -1439,6 +1447,10 @@ void endStep(dfr_context *c) { c->finished = (c->time >= c->cfg.target_time + c-
 void fluidStep(dfr_context *c) {
   beginStep(c);
   const double h = c->h;  // OLD h (:535)
+  if (c->cfg.use_rigid_contact_solver) {  // performNeighborhoodSearch (:2044-2056): z-sort every 500 steps
+    if (c->sortCounter % 500 == 0) contactSort(c);
+    c->sortCounter++;
+  }
   findNeighbors(c);
   computeDensities(c);
   computeDFSPHFactor(c);
@@ -1647,10 +1659,10 @@ int orc_finalize(dfr_context *c) {
   if (!c || c->finalized) return fail(c, DFR_ERR_STATE, "already finalized");
   if (c->x.empty() && c->nfCapacity == 0) orc_set_fluid(c, 0, nullptr, nullptr);
   c->mgr.init((int)c->bodies.size());
+  contactInit(c);                    // RigidContactSolver ctor + first z-sort: before the particles are moved to world space (:250-257)
   updateBoundaryParticles(c, true);  // RigidBody3dBoundarySimulator::deferredInit (:256-262)
   updateBoundaryVolume(c);
   snapshot(c);
-  contactInit(c);
   c->finalized = true;
   return DFR_OK;
 }
@@ -1693,10 +1705,10 @@ int orc_reset(dfr_context *c) {  // SimulatorBase::reset (SimulatorBase.cpp:887-
     e.nextEmitTime = e.emitStart;
     e.emitCounter = 0;
   }
+  contactReset(c);  // incl. the z-sort of RigidBody3dBoundarySimulator::reset (:358), which sees the stale particle positions
   updateBoundaryParticles(c, true);
   updateBoundaryVolume(c);
   c->mgr.reset();
-  contactReset(c);
   c->time = 0.0;
   c->h = c->cfg.time_step_size;
   c->iterations = c->iterationsV = c->step_count = 0;

@@ -29,6 +29,11 @@ CASES = {
                           dict(steps=8, init_v=(0.8, -0.5, 0.1), init_omega=(1.0, 2.0, -0.5), load_state=True)),
     "cfl_iter_nowarm_nogyro": (dict(n_target=1200, n_boxes=1), dict(cfl_method=2, use_pressure_warmstart=0, use_divergence_warmstart=0, rigid_body_mode=1,
                                                                     gradient_mode=2, max_error=0.05, target_time=0.05), dict(steps=6)),
+    # penalty rigid-rigid contact + friction + manager (BASELINE.json configs[2]); reset() after step 4 exercises the
+    # history-dependent contact order of the reference (oracle/oracle_contact.inc)
+    "contact_manager_2box": (dict(n_target=1500), dict(surface_tension_method=2, surface_tension=0.3, max_error=0.05, target_time=0.05,
+                                                       use_rigid_gradient_manager=1, use_rigid_contact_solver=1, rigid_contact_beta=2000.0,
+                                                       rigid_contact_friction=0.4), dict(steps=8, scene="contact", reset_at=4)),
 }
 
 
@@ -38,7 +43,7 @@ def run_case(name):
 
     rlib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref.so"))
     skw, cfg, extra = CASES[name]
-    sc = scenes.dam_break_scene(**skw)
+    sc = scenes.contact_scene(**skw) if extra.get("scene") == "contact" else scenes.dam_break_scene(**skw)
     if "init_v" in extra:
         sc["bodies"][1]["init_v"] = extra["init_v"]
         sc["bodies"][1]["init_omega"] = extra["init_omega"]
@@ -74,7 +79,11 @@ def run_case(name):
     body_grads = {b: [] for b in dyn}
     body_ft = {b: [] for b in dyn}
     mgr = []
+    if "reset_at" in extra:
+        out["reset_at"] = extra["reset_at"]
     for s in range(extra["steps"]):
+        if s == extra.get("reset_at", -1):
+            ctx.reset()
         ctx.step(1)
         info = ctx.step_info()
         per_step["time"].append(info.time)

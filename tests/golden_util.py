@@ -55,7 +55,10 @@ def replay_and_compare(factory, name, state_tol, grad_tol):
         assert np.array_equal(cnt, g[f"nbr_{key}_counts"]), ("neighbour counts", key)
         assert np.array_equal(idx, g[f"nbr_{key}_indices"]), ("neighbour sets", key)
     steps = int(g["steps"])
+    reset_at = int(g["reset_at"]) if "reset_at" in g.files else -1
     for s in range(steps):
+        if s == reset_at:
+            ctx.reset()
         ctx.step(1)
         info = ctx.step_info()
         assert info.iterations == int(g["step_iters"][s]) and info.iterations_v == int(g["step_iters_v"][s]), (s, info.iterations, info.iterations_v)
