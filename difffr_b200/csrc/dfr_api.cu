@@ -14,6 +14,7 @@
 #include "../../include/dfr.h"
 #include "dfr_kernels.cuh"
 #include "dfr_rigid.cuh"
+#include "dfr_contact.cuh"
 
 using namespace dfr;
 
@@ -104,6 +105,16 @@ struct dfr_context {
   DevBuf<unsigned int> off_d;
   int cap_f = 0, cap_b = 0;  // ELL row capacities (neighbours per particle)
   unsigned int cap_d = 0;
+
+  // penalty rigid-rigid contact (dfr_contact.cuh)
+  ContactParams CP;
+  DevBuf<double> c_vol0, c_dens0, c_dens, c_records;
+  DevBuf<double4> c_vel;
+  DevBuf<int> c_order;
+  std::vector<int> h_order;         // per dynamic body: particles (relative to dyn_begin) in the reference's storage order
+  std::vector<double4> h_dynpos;    // scratch for the z-sort keys
+  long long sort_counter = 0;       // TimeStepDiffDFSPH::m_counter
+  bool contact_ready = false;
 
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
@@ -419,9 +430,87 @@ int launch_solver(dfr_context *c) {
   return DFR_OK;
 }
 
+// ---- contact order: the reference applies the contact impulses in its storage order, which CompactNSearch's z_sort
+// (a stable sort by the Morton code of floor(x / support radius)) permutes at deferredInit (body-frame positions), at
+// every reset (positions left by the previous trajectory) and every 500 steps; see oracle/oracle_contact.inc ----
+void contact_sort_with(dfr_context *c, const std::vector<double4> &pos) {
+  const double r = c->P.support_radius;
+  auto spread3 = [](uint64_t v) {
+    uint64_t o = 0;
+    for (int k = 0; k < 21; k++) o |= ((v >> k) & 1ull) << (3 * k);
+    return o;
+  };
+  const long long B = 1ll << 20;
+  std::vector<uint64_t> code(pos.size());
+  for (size_t i = 0; i < pos.size(); i++) {
+    const long long cx = (long long)std::floor(pos[i].x / r), cy = (long long)std::floor(pos[i].y / r), cz = (long long)std::floor(pos[i].z / r);
+    code[i] = spread3((uint64_t)(cx + B)) | (spread3((uint64_t)(cy + B)) << 1) | (spread3((uint64_t)(cz + B)) << 2);
+  }
+  for (auto &hb : c->bodies) {
+    if (!hb.dynamic) continue;
+    const int first = hb.dev0.p_begin - c->dyn_begin;
+    std::stable_sort(c->h_order.begin() + first, c->h_order.begin() + first + hb.n, [&](int a, int b) { return code[a] < code[b]; });
+  }
+}
+int contact_upload_order(dfr_context *c) {
+  if (c->n_dyn_p == 0) return DFR_OK;
+  CU(cudaMemcpyAsync(c->c_order.p, c->h_order.data(), c->n_dyn_p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DFR_OK;
+}
+int contact_sort_current(dfr_context *c) {  // keys from the current world positions of the dynamic particles
+  if (c->n_dyn_p == 0) return DFR_OK;
+  c->h_dynpos.resize(c->n_dyn_p);
+  CU(cudaMemcpyAsync(c->h_dynpos.data(), c->bpos.p + c->dyn_begin, c->n_dyn_p * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  contact_sort_with(c, c->h_dynpos);
+  return contact_upload_order(c);
+}
+// RigidContactSolver ctor (:23-263): rest volumes / densities, then the first z-sort (body-frame positions)
+int contact_init(dfr_context *c) {
+  const size_t NB = (size_t)std::max(c->n_b, 1), ND = (size_t)std::max(c->n_dyn_p, 1);
+  CU(c->c_vol0.alloc(NB)); CU(c->c_dens0.alloc(NB)); CU(c->c_dens.alloc(ND)); CU(c->c_vel.alloc(ND)); CU(c->c_order.alloc(ND));
+  CU(c->c_records.alloc(ND * CREC_N));
+  const double hc = c->cfg.rigid_contact_support_radius_factor * c->cfg.particle_radius;
+  c->CP.inv_h = 1.0 / hc;
+  c->CP.k_cubic = 8.0 / (M_PI * hc * hc * hc);
+  c->CP.gamma = c->cfg.rigid_contact_gamma;
+  c->CP.beta = c->cfg.rigid_contact_beta;
+  c->CP.mu = c->cfg.rigid_contact_friction;
+  if (hc > c->P.support_radius * (1.0 + 1e-12))
+    return fail(c, DFR_ERR_INVALID, "rigidContactSupportRadiusFactor above 4: the reference searches contacts with the fluid support radius");
+  c->h_order.resize(c->n_dyn_p);
+  std::vector<double4> local(c->n_dyn_p);
+  for (auto &hb : c->bodies) {
+    if (!hb.dynamic) continue;
+    const int first = hb.dev0.p_begin - c->dyn_begin;
+    for (int64_t j = 0; j < hb.n; j++) {
+      c->h_order[first + j] = first + (int)j;
+      local[first + j] = make_double4(hb.x_local[3 * j], hb.x_local[3 * j + 1], hb.x_local[3 * j + 2], 0.0);
+    }
+  }
+  contact_sort_with(c, local);
+  return DFR_OK;
+}
+// vol0 / density0 from the (rigidly moved, hence equal up to rounding) world-space samples; needs the cell tables
+int contact_rest_state(dfr_context *c) {
+  if (c->n_b == 0) return DFR_OK;
+  for (int pass = 0; pass < 2; pass++)
+    LAUNCH(c, k_contact_rest, cdiv(c->n_b, 128), 128, c->P, c->CP, pass, c->bpos.p, c->bbody.p, c->n_b, c->n_static_p, grid_static(c),
+           grid_dyn(c), c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->c_vol0.p, c->c_dens0.p);
+  return DFR_OK;
+}
+
 // one SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169)
 int launch_step(dfr_context *c) {
   const int n = c->launch_nf, g = cdiv(n, 128);
+  if (c->cfg.use_rigid_contact_solver) {  // TimeStepDiffDFSPH::performNeighborhoodSearch (:2044-2056): z-sort every 500 steps
+    if (c->sort_counter % 500 == 0) {
+      int rc = contact_sort_current(c);
+      if (rc) return rc;
+    }
+    c->sort_counter++;
+  }
   LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p);
   int rc = build_neighbors(c);
   if (rc) return rc;
@@ -455,17 +544,45 @@ int launch_step(dfr_context *c) {
   }
   if (c->P.n_bodies > 0) {
     LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
-    LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p);
+    if (c->cfg.use_rigid_contact_solver) {
+      LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_PRE);
+      if (c->n_dyn_p > 0) {
+        const int gd = cdiv(c->n_dyn_p, 128);
+        LAUNCH(c, k_contact_prepare, gd, 128, c->P, c->CP, c->dBodies.p, c->bpos.p, c->bbody.p, c->dyn_begin, c->n_dyn_p, c->n_static_p,
+               grid_static(c), grid_dyn(c), c->n_static_p > 0 ? 1 : 0, c->c_vol0.p, c->c_vel.p, c->c_dens.p);
+        LAUNCH(c, k_contact_force, gd, 128, c->P, c->CP, c->dBodies.p, c->bpos.p, c->bx0.p, c->bbody.p, c->dyn_begin, c->n_dyn_p,
+               c->n_static_p, grid_static(c), grid_dyn(c), c->n_static_p > 0 ? 1 : 0, c->c_vol0.p, c->c_dens0.p, c->c_vel.p, c->c_dens.p,
+               c->c_records.p);
+        if (c->profiling) prof_begin(c, "k_contact_apply");
+        k_contact_apply<<<c->P.n_bodies, 32, (1 + c->P.n_bodies) * CG_N * sizeof(double), c->stream>>>(
+            c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, c->bpos.p, c->dyn_begin, c->c_order.p, c->c_records.p);
+        if (c->profiling) prof_end(c);
+        c->launches++;
+      }
+      LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_POST);
+    } else {
+      LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_ALL);
+    }
     if (c->n_dyn_p > 0)
       LAUNCH(c, k_update_boundary_particles, cdiv(c->n_dyn_p, 128), 128, c->dBodies.p, c->bbody.p, c->bx0.p, c->bpos.p, c->bvel.p,
              c->dyn_begin, c->n_dyn_p, 0);
   } else {
-    LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p);
+    LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_ALL);
   }
   return DFR_OK;
 }
 
 int reset_device_state(dfr_context *c) {
+  if (c->cfg.use_rigid_contact_solver) {
+    if (!c->contact_ready) {
+      int rc = contact_init(c);
+      if (rc) return rc;
+    } else {  // RigidBody3dBoundarySimulator::reset (:346-362): z-sort before the particles return to their start pose
+      int rc = contact_sort_current(c);
+      if (rc) return rc;
+    }
+    c->sort_counter = 0;
+  }
   // fluid: initial state back into the current buffers (id order)
   const size_t n = (size_t)c->nf0;
   c->cur = 0;
@@ -522,6 +639,15 @@ int reset_device_state(dfr_context *c) {
   if (rc) return rc;
   rc = compute_boundary_volumes(c);
   if (rc) return rc;
+  if (c->cfg.use_rigid_contact_solver) {
+    if (!c->contact_ready) {
+      rc = contact_rest_state(c);
+      if (rc) return rc;
+      c->contact_ready = true;
+    }
+    rc = contact_upload_order(c);
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->spec_div = 1;
   c->spec_prs = std::max(2, c->cfg.min_iterations);
@@ -606,6 +732,7 @@ void dfr_destroy(dfr_context *c) {
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
+  c->c_vol0.free(); c->c_dens0.free(); c->c_dens.free(); c->c_records.free(); c->c_vel.free(); c->c_order.free();
   for (auto &p : c->prof_pending) {
     cudaEventDestroy(p.e0);
     cudaEventDestroy(p.e1);
@@ -690,7 +817,6 @@ int dfr_add_emitter(dfr_context *c, int width, int height, const double position
 int dfr_finalize(dfr_context *c) {
   if (!c) return DFR_ERR_INVALID;
   if (c->finalized) return fail(c, DFR_ERR_STATE, "already finalized");
-  if (c->cfg.use_rigid_contact_solver) return fail(c, DFR_ERR_INVALID, "rigid contact solver not implemented in the CUDA path yet");
   cudaSetDevice(c->device);
   const dfr_config &cfg = c->cfg;
   Params &P = c->P;

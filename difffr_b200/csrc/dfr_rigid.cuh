@@ -293,21 +293,59 @@ __device__ inline void mgr_position_rotation_chain(const Params &P, BodyDev *bod
 // End of TimeStepDiffDFSPH::step (time advance :645, backwardPerStep :493-524, endStep :432-490) followed by
 // the rest of SimulatorBase::timeStepNoGUI (:1159-1169): manager stages, BoundarySimulator::updateBoundaryForces
 // (BoundarySimulator.cpp:10-36), RigidBody3dBoundarySimulator::velocityTimeStep / positionTimeStep (:278-344).
-__global__ void k_body_update(const __grid_constant__ Params P, StepState *st, BodyDev *bodies, MgrBlock *M) {
+// phase: BODY_ALL (no contact solver) runs the whole sequence; with the penalty contact solver the sequence is cut in
+// two around the contact kernels (dfr_contact.cuh): BODY_PRE ends after addGravity (RigidBody3dBoundarySimulator.cpp:
+// 284-296, gravity first and without the isAnimated test), BODY_POST starts at the repeated updateBoundaryForces
+// (RigidContactSolver.cpp:357-360).
+enum { BODY_ALL = 0, BODY_PRE = 1, BODY_POST = 2 };
+
+__global__ void k_body_update(const __grid_constant__ Params P, StepState *st, BodyDev *bodies, MgrBlock *M, int phase) {
   const double h = st->h;  // NEW h: backwardPerStep, the manager and the rigid integrator re-read the TimeManager
   const int b = threadIdx.x;
-  if (b == 0) {
+  const int n = P.n_bodies;
+  if (b == 0 && phase != BODY_POST) {
     st->last_iters = st->prs_iters;
     st->total_iters += st->prs_iters;
     st->total_particle_steps += st->nf;
     st->time += st->h_step;
     st->finished = (st->time >= P.target_time + P.uniform_acc_time) ? 1 : 0;
   }
+  const d3 g = mk3(P.gx, P.gy, P.gz);
+  if (phase == BODY_POST) {
+    if (b != 0) return;
+    // updateBoundaryForces() once per boundary model: the first call applies the fluid force, each later call adds a
+    // zero torque, i.e. one more gyroscopic increment (addTorque), and overwrites the getForce()/getTorque() backup
+    for (int rep = 0; rep < n; rep++)
+      for (int R = 0; R < n; R++) {
+        BodyDev &B = bodies[R];
+        if (!B.dynamic) continue;
+        if (!B.animated) {
+          rb_add_force(B, B.force, h);
+          rb_add_torque(P, B, B.torque, h);
+        }
+        B.force_last = B.force;
+        B.torque_last = B.torque;
+        B.force = mk3(0, 0, 0);
+        B.torque = mk3(0, 0, 0);
+      }
+    if (P.use_manager) {  // after_Rigid_Rigid_coupling_step (RigidBodyGradientManager.cpp:460-468)
+      mgr_force_torque_chain(P, bodies, M, true);
+      mgr_velocity_chain(P, bodies, M, h);  // sees the cleared force slots
+      mgr_position_rotation_chain(P, bodies, M, h);
+    }
+    for (int R = 0; R < n; R++)
+      if (bodies[R].dynamic) rb_animate(bodies[R], h);
+    return;
+  }
   if (!P.use_manager) {
-    if (b < P.n_bodies) {
+    if (b < n) {
       BodyDev &B = bodies[b];
       if (B.dynamic) {
         if (!B.animated) perform_chain_rule(P, B, h);
+        if (phase == BODY_PRE) {
+          rb_add_force(B, B.mass * g, h);
+          return;
+        }
         // velocityTimeStep (no contact solver)
         if (!B.animated) {
           rb_add_force(B, B.force, h);
@@ -317,12 +355,11 @@ __global__ void k_body_update(const __grid_constant__ Params P, StepState *st, B
         B.torque_last = B.torque;
         B.force = mk3(0, 0, 0);
         B.torque = mk3(0, 0, 0);
-        if (!B.animated) rb_add_force(B, B.mass * mk3(P.gx, P.gy, P.gz), h);
+        if (!B.animated) rb_add_force(B, B.mass * g, h);
         rb_animate(B, h);
       }
     }
   } else if (b == 0) {
-    const int n = P.n_bodies;
     for (int R = 0; R < n; R++) {
       BodyDev &B = bodies[R];
       if (B.dynamic && !B.animated) {  // update_rigid_body_gradient_manager (BoundaryModel_Akinci2012.cpp:952-967)
@@ -333,6 +370,11 @@ __global__ void k_body_update(const __grid_constant__ Params P, StepState *st, B
     }
     mgr_force_torque_chain(P, bodies, M, false);
     mgr_velocity_chain(P, bodies, M, h);
+    if (phase == BODY_PRE) {
+      for (int R = 0; R < n; R++)
+        if (bodies[R].dynamic) rb_add_force(bodies[R], bodies[R].mass * g, h);
+      return;
+    }
     for (int R = 0; R < n; R++) {
       BodyDev &B = bodies[R];
       if (!B.dynamic) continue;
@@ -347,7 +389,7 @@ __global__ void k_body_update(const __grid_constant__ Params P, StepState *st, B
     }
     for (int R = 0; R < n; R++) {
       BodyDev &B = bodies[R];
-      if (B.dynamic && !B.animated) rb_add_force(B, B.mass * mk3(P.gx, P.gy, P.gz), h);
+      if (B.dynamic && !B.animated) rb_add_force(B, B.mass * g, h);
     }
     mgr_position_rotation_chain(P, bodies, M, h);
     for (int R = 0; R < n; R++)

@@ -1667,6 +1667,7 @@ int orc_finalize(dfr_context *c) {
   return DFR_OK;
 }
 
+int orc_reset(dfr_context *c);
 int orc_load_fluid_state(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   const int64_t n = c->nfActive0;
@@ -1675,7 +1676,7 @@ int orc_load_fluid_state(dfr_context *c, const double *x, const double *v, const
   if (kappa) std::memcpy(c->kappa.data(), kappa, sizeof(double) * n);
   if (kappa_v) std::memcpy(c->kappaV.data(), kappa_v, sizeof(double) * n);
   snapshot(c);
-  return DFR_OK;
+  return orc_reset(c);  // checkLoadState is part of SimulatorBase::reset (SimulatorBase.cpp:887-934); the reference driver resets too
 }
 
 int orc_reset(dfr_context *c) {  // SimulatorBase::reset (SimulatorBase.cpp:887-934)
