@@ -116,6 +116,11 @@ struct dfr_context {
   long long sort_counter = 0;       // TimeStepDiffDFSPH::m_counter
   bool contact_ready = false;
 
+  // SM-local scheduling of the gather kernels (dfr_kernels.cuh: VSched)
+  DevBuf<unsigned int> sched_ctr;
+  int sched_parity = 0, nsm = 1;
+  std::map<const void *, int> resident_blocks;
+
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
   double device_ms = 0.0;
@@ -200,6 +205,43 @@ void prof_resolve(dfr_context *c, int used_div, int used_prs) {
       if ((c)->profiling) prof_end((c));                           \
       (c)->launches++;                                             \
     }                                                              \
+  } while (0)
+
+// persistent launch of a gather kernel: SMs x resident blocks CTAs walk `nvb` virtual 128-particle blocks
+VSched next_sched(dfr_context *c, int nvb) {
+  VSched S;
+  S.ctr = c->sched_ctr.p;
+  S.parity = c->sched_parity;
+  c->sched_parity ^= 1;
+  S.nsm = c->nsm;
+  S.nvb = nvb;
+  S.per = (nvb + c->nsm - 1) / c->nsm;
+  return S;
+}
+template <class K>
+int persistent_grid(dfr_context *c, K kernel, int nvb) {
+#if DFR_SM_LOCAL
+  auto it = c->resident_blocks.find((const void *)kernel);
+  if (it == c->resident_blocks.end()) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 128, 0) != cudaSuccess || nb < 1) nb = 1;
+    it = c->resident_blocks.emplace((const void *)kernel, nb).first;
+  }
+  return std::max(1, std::min(nvb, c->nsm * it->second));
+#else
+  (void)kernel;
+  return nvb;
+#endif
+}
+#define PLAUNCH(c, kernel, nvb, ...)                                                          \
+  do {                                                                                        \
+    if ((nvb) > 0) {                                                                          \
+      const int pg__ = persistent_grid((c), kernel, (nvb));                                   \
+      if ((c)->profiling) prof_begin((c), #kernel);                                           \
+      kernel<<<pg__, 128, 0, (c)->stream>>>(__VA_ARGS__, next_sched((c), (nvb)));             \
+      if ((c)->profiling) prof_end((c));                                                      \
+      (c)->launches++;                                                                        \
+    }                                                                                         \
   } while (0)
 
 int scan_u32(dfr_context *c, unsigned int *data, size_t n, unsigned int *total) {
@@ -324,7 +366,7 @@ int build_neighbors(dfr_context *c) {
   c->vcur = 1 - c->vcur;
   rc = build_dyn_grid(c);
   if (rc) return rc;
-  LAUNCH(c, k_nbr_build, cdiv(n, 128), 128, c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+  PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
@@ -394,11 +436,11 @@ int launch_solver(dfr_context *c) {
       c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p
 #define PUSH_ARGS c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0
   if (warm) {
-    LAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, 128, RHO_ARGS);
+    PLAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, RHO_ARGS);
     launch_boundary_side<PRESSURE>(c, false, 0);
-    LAUNCH(c, (k_push<PRESSURE, false>), g, 128, PUSH_ARGS);
+    PLAUNCH(c, (k_push<PRESSURE, false>), g, PUSH_ARGS);
   }
-  LAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, 128, RHO_ARGS);
+  PLAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, RHO_ARGS);
   const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
   int launched = 0;
   int spec = PRESSURE ? c->spec_prs : c->spec_div;
@@ -408,8 +450,8 @@ int launch_solver(dfr_context *c) {
       c->prof_solver = PRESSURE ? 1 : 0;
       c->prof_iter = launched + it;
       launch_boundary_side<PRESSURE>(c, true, 1);
-      LAUNCH(c, (k_push<PRESSURE, true>), g, 128, PUSH_ARGS);
-      LAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, 128, RHO_ARGS);
+      PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
+      PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
     }
     c->prof_solver = -1;
     launched += spec;
@@ -515,7 +557,7 @@ int launch_step(dfr_context *c) {
   int rc = build_neighbors(c);
   if (rc) return rc;
   int a = c->cur;
-  LAUNCH(c, k_density_factor, g, 128, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
+  PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
          c->sgp.p, c->xrho.p);
   bool scale_kv = false;
   if (c->cfg.enable_divergence_solver) {
@@ -524,8 +566,8 @@ int launch_step(dfr_context *c) {
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
   if (c->cfg.surface_tension_method == 2)
-    LAUNCH(c, k_normals, g, 128, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
-  LAUNCH(c, k_nonpressure, g, 128, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+    PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
+  PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
          c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
   c->vcur = 1 - c->vcur;
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
@@ -732,6 +774,7 @@ void dfr_destroy(dfr_context *c) {
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
+  c->sched_ctr.free();
   c->c_vol0.free(); c->c_dens0.free(); c->c_dens.free(); c->c_records.free(); c->c_vel.free(); c->c_order.free();
   for (auto &p : c->prof_pending) {
     cudaEventDestroy(p.e0);
@@ -933,6 +976,12 @@ int dfr_finalize(dfr_context *c) {
   CU(c->dEmitters.alloc(std::max<size_t>(c->h_emitters.size(), 1)));
   const int nc = P.grid.ncells;
   CU(c->dSt.alloc(1));
+  CU(c->sched_ctr.alloc(2 * DFR_SCHED_STRIDE));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    c->nsm = std::max(1, std::min(prop.multiProcessorCount, (int)DFR_SCHED_STRIDE));
+  }
   for (int k = 0; k < 2; k++) {
     CU(c->pos[k].alloc(N)); CU(c->vel[k].alloc(N)); CU(c->kappa[k].alloc(N)); CU(c->kappav[k].alloc(N));
     CU(c->pid[k].alloc(N)); CU(c->pstate[k].alloc(N));

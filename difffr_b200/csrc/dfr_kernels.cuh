@@ -33,6 +33,72 @@ struct Rec3 {
 };
 #define DFR_FULL 0xffffffffu
 
+// ---------------------------------------------------------------------------------------------
+// SM-local block scheduling for the neighbour-gather kernels.  A plain grid hands consecutive 128-particle blocks
+// to different SMs, so the ~8 blocks resident on one SM gather from 8 unrelated neighbourhoods and thrash its L1
+// (profiles/r1d: 60 % L1 hit rate although a block re-uses every line ~16 times).  Here the grid is persistent
+// (SMs x resident blocks) and every SM owns one contiguous range of virtual blocks: its resident CTAs claim
+// consecutive blocks of that range, i.e. spatially adjacent particles whose neighbourhoods overlap.  A CTA that runs
+// out of work sweeps the other SMs' ranges, so every block is processed no matter how CTAs were placed.
+// Two counter sets alternate between launches; each launch clears the set the next one will use.
+// MEASURED (profiles/r1e_sm_local_experiment.md, B200, 1 M particles): L1 hit rate 62 -> 77 %, L2 reads -30 %, but the
+// step got SLOWER (3.81 -> 5.09 ms): the gather kernels are bound by L1 wavefronts per gather (~16 lines per warp-wide
+// gather), not by the hit rate, and the per-block barriers of a persistent CTA add stalls.  Kept as a build option
+// (-DDFR_SM_LOCAL=1), off by default.
+// ---------------------------------------------------------------------------------------------
+#ifndef DFR_SM_LOCAL
+#define DFR_SM_LOCAL 0
+#endif
+#define DFR_SCHED_STRIDE 256
+struct VSched {
+  unsigned int *ctr;  // [2][DFR_SCHED_STRIDE]
+  int parity, nsm, per, nvb;
+};
+__device__ __forceinline__ void vsched_prologue(const VSched &S) {
+#if DFR_SM_LOCAL
+  if (blockIdx.x == 0)
+    for (int t = threadIdx.x; t < DFR_SCHED_STRIDE; t += blockDim.x) S.ctr[(1 - S.parity) * DFR_SCHED_STRIDE + t] = 0u;
+#endif
+}
+struct VState {
+  int sm, tried;
+};
+__device__ __forceinline__ VState vsched_begin(const VSched &S) {
+  VState v;
+  unsigned int smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  v.sm = (int)(smid % (unsigned int)S.nsm);
+  v.tried = 0;
+  return v;
+}
+__device__ __forceinline__ int vsched_next(const VSched &S, VState &v, int *sh) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int vb = -1;
+    while (v.tried < S.nsm) {
+      const unsigned int k = atomicAdd(&S.ctr[S.parity * DFR_SCHED_STRIDE + v.sm], 1u);
+      const long long cand = (long long)v.sm * S.per + k;
+      if (k < (unsigned int)S.per && cand < S.nvb) {
+        vb = (int)cand;
+        break;
+      }
+      v.sm = (v.sm + 1 == S.nsm) ? 0 : v.sm + 1;
+      v.tried++;
+    }
+    *sh = vb;
+  }
+  __syncthreads();
+  return *sh;
+}
+#if DFR_SM_LOCAL
+#define DFR_VB_LOOP(S)               \
+  __shared__ int vb_sh_;             \
+  VState vb_state_ = vsched_begin(S); \
+  for (int vb_ = vsched_next(S, vb_state_, &vb_sh_); vb_ >= 0; vb_ = vsched_next(S, vb_state_, &vb_sh_))
+#else
+#define DFR_VB_LOOP(S) for (int vb_ = blockIdx.x, once_ = 1; once_; once_ = 0)
+#endif
+
 // read-only 32-byte record load as ONE 256-bit instruction (sm_100: LDG.E.ENL2.256.CONSTANT).  A gathered
 // record then costs one L1 tag/data wavefront per distinct 128-byte line instead of two (profiles/r1a: the
 // neighbour passes are bound by L1 data-stage wavefronts, not by HBM or the FP64 pipe).
@@ -405,9 +471,11 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
 // host then grows the capacity and replays the step (dfr_api.cu: launch_step).
 __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
                                                     GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
-                                                    int *idx_f, int *idx_b, int cap_f, int cap_b) {
+                                                    int *idx_f, int *idx_b, int cap_f, int cap_b, const VSched S) {
+  vsched_prologue(S);
   const int n = st->nf;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  DFR_VB_LOOP(S) {
+  const int i = vb_ * 128 + threadIdx.x;
   int cf = 0, cb = 0;
   if (i < n) {
     const int lane = i & 31;
@@ -437,6 +505,7 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
     atomicAdd((unsigned long long *)&st->total_neighbors, (unsigned long long)tot);
     if ((unsigned int)mf > st->list_used_f) atomicMax(&st->list_used_f, (unsigned int)mf);
     if ((unsigned int)mb > st->list_used_b) atomicMax(&st->list_used_b, (unsigned int)mb);
+  }
   }
 }
 // dynamic boundary particle -> fluid neighbours, CSR rows (one warp later walks one row)
@@ -498,9 +567,12 @@ __global__ void k_store_volume(double4 *bpos, const double *vol, int n_b) {
 // computeDFSPHFactor, TimeStepDiffDFSPH.cpp:883-962)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ Params P, const StepState *st, const double4 *pos, const double4 *bpos,
-                                                         NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp, double4 *xrho) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= st->nf) return;
+                                                         NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp, double4 *xrho,
+                                                         const VSched S) {
+  vsched_prologue(S);
+  DFR_VB_LOOP(S) {
+  const int i = vb_ * 128 + threadIdx.x;
+  if (i >= st->nf) continue;
   const double4 pi = pos[i];
   double dens = P.volume * P.W_zero;
   double S = 0.0;
@@ -531,6 +603,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
   const double denom = S + dot(G, G);
   factor[i] = (denom > DFR_EPS) ? -1.0 / denom : 0.0;
   sgp[i] = make_double4(-G.x, -G.y, -G.z, 0.0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -543,13 +616,15 @@ enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
 template <bool PRESSURE, int MODE>
 __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
-                                              const int *state, double *kappa, double *dadv, double4 *xk, double *partials) {
+                                              const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const VSched S) {
+  vsched_prologue(S);
   if (MODE == RHO_ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
   const int nf = st->nf;
-  if ((int)(blockIdx.x * blockDim.x) >= nf) return;  // grids are sized for the emitter capacity; only live blocks take a ticket
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  DFR_VB_LOOP(S) {
+  if (vb_ * 128 >= nf) continue;  // grids are sized for the emitter capacity; only live blocks take a ticket
+  const int i = vb_ * 128 + threadIdx.x;
   const double h = PRESSURE ? st->h : st->h_step;
   double err = 0.0;
   if (i < nf) {
@@ -608,7 +683,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-      partials[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+      partials[vb_] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
       __threadfence();
       const unsigned int nblk = (unsigned int)((nf + 127) / 128);
       const unsigned int t = atomicAdd(&st->ticket, 1u);
@@ -648,6 +723,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
       }
     }
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -657,13 +733,16 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 template <bool PRESSURE, bool ITER>
 __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
-                                               NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa) {
+                                               NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa,
+                                               const VSched S) {
+  vsched_prologue(S);
   if (ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= st->nf) return;
-  if (state[i] != 0) return;
+  DFR_VB_LOOP(S) {
+  const int i = vb_ * 128 + threadIdx.x;
+  if (i >= st->nf) continue;
+  if (state[i] != 0) continue;
   const double h = PRESSURE ? st->h : st->h_step;
   const double4 pi = xk[i];
   const double ki = pi.w;
@@ -693,6 +772,7 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
   v.y += dv.y;
   v.z += dv.z;
   vel[i] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -902,9 +982,11 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_co
 // maximum (Simulation.cpp:542-575), fused.  kappa_v *= h_step of divergenceSolve (:870-880) rides along.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params P, const StepState *st, const double4 *xrho, NbrList lf,
-                                                  double4 *normal) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= st->nf) return;
+                                                  double4 *normal, const VSched S) {
+  vsched_prologue(S);
+  DFR_VB_LOOP(S) {
+  const int i = vb_ * 128 + threadIdx.x;
+  if (i >= st->nf) continue;
   const double4 pi = xrho[i];
   d3 n = mk3(0, 0, 0);
   for_neighbors4(
@@ -916,15 +998,18 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
       });
   // w carries the particle's density so that the force pass gathers (n_j, rho_j) in one record
   stg4(normal + i, make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, pi.w));
+  }
 }
 
 __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
                                                       const double4 *bvel, NbrList lf, NbrList lb,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
-                                                      double4 *acc_out, double4 *vel_out) {
+                                                      double4 *acc_out, double4 *vel_out, const VSched S) {
+  vsched_prologue(S);
   const int nf = st->nf;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double h = st->h_step;
+  DFR_VB_LOOP(S) {
+  const int i = vb_ * 128 + threadIdx.x;
   double mag = 0.0;
   if (i < nf) {
     const double4 pi = xrho[i];
@@ -1001,6 +1086,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
   if (threadIdx.x == 0) {
     const double m = fmax(fmax(wmax[0], wmax[1]), fmax(wmax[2], wmax[3]));
     atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(m));
+  }
   }
 }
 
