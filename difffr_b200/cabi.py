@@ -95,7 +95,7 @@ SYMBOLS = [
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
     "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
-    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode",
+    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_unique_id", "slab_configure", "slab_info",
 ]
 
 GRAD_NAMES = [
@@ -209,6 +209,10 @@ class Context:
         proto("get_neighbors", C.c_int, vp, C.c_int, C.c_int, ip, ip, i64, C.POINTER(i64))
         proto("add_emitter", C.c_int, vp, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double)
         proto("get_device_time_ms", C.c_int, vp, dp, C.POINTER(i64))
+        if hasattr(L, p + "slab_configure"):  # multi-GPU entry points of the CUDA library only
+            proto("slab_unique_id", C.c_int, C.c_char_p)
+            proto("slab_configure", C.c_int, vp, C.c_int, C.c_int, C.c_char_p)
+            proto("slab_info", C.c_int, vp, C.POINTER(i64))
         proto("reset_gradient", C.c_int, vp)
         proto("set_gradient_mode", C.c_int, vp, C.c_int)
         if hasattr(L, p + "set_profiling"):  # the CPU oracle has no kernels to profile
@@ -259,6 +263,23 @@ class Context:
         v0 = _f64(v0, (3,))
         w0 = _f64(omega0, (3,))
         self._check(self._fn("set_init_v_omega")(self._ctx, int(body), _dptr(v0), _dptr(w0)))
+
+    def slab_unique_id(self) -> bytes:
+        """NCCL unique id for `slab_configure` (call on rank 0, broadcast the bytes to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        rc = self._fn("slab_unique_id")(buf)
+        if rc != 0:
+            raise DfrError(rc, "dfr_slab_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def slab_configure(self, rank, n_ranks, id_bytes):
+        """Make this context slab `rank` of `n_ranks` of the scene (before finalize; every rank builds the same scene)."""
+        self._check(self._fn("slab_configure")(self._ctx, int(rank), int(n_ranks), C.c_char_p(bytes(id_bytes))))
+
+    def slab_info(self):
+        out = (C.c_int64 * 4)()
+        self._check(self._fn("slab_info")(self._ctx, out))
+        return {"owned": out[0], "ghosts": out[1], "exchanged_bytes": out[2], "slabs": out[3]}
 
     def finalize(self):
         self._check(self._fn("finalize")(self._ctx))

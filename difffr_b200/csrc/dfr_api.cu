@@ -15,6 +15,10 @@
 #include "dfr_kernels.cuh"
 #include "dfr_rigid.cuh"
 #include "dfr_contact.cuh"
+#include "dfr_slab.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace dfr;
 
@@ -67,7 +71,9 @@ struct dfr_context {
 
   // host-side scene description
   std::vector<double> h_fx, h_fv;
-  int64_t nf0 = 0, nf_cap = 0;
+  int64_t nf0 = 0, nf_cap = 0;  // nf0: fluid particles of the scene
+  int64_t nf_loc0 = 0;          // of those, held by this context at t = 0 (all of them unless slab-decomposed)
+  std::vector<int> h_ids0;      // their ids (slab mode)
   std::vector<HostBody> bodies;
   std::vector<EmitterDev> h_emitters;
   DevBuf<EmitterDev> dEmitters;
@@ -115,6 +121,22 @@ struct dfr_context {
   std::vector<double4> h_dynpos;    // scratch for the z-sort keys
   long long sort_counter = 0;       // TimeStepDiffDFSPH::m_counter
   bool contact_ready = false;
+
+  // slab decomposition over several GPUs (dfr_slab.cuh); NCCL is loaded at run time so that single-GPU use needs none
+  struct Slab {
+    bool on = false;
+    int rank = 0, n = 1;
+    ncclComm_t comm = nullptr;
+    SlabGeom G;
+    std::vector<int> own0;               // ids owned at t = 0
+    int h_ranges[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int send_cap = 0;
+    DevBuf<double4> s_pos[2], s_vel[2], s_misc[2], r_misc;
+    DevBuf<int> counts;                  // [0..1] my export counts, [2..3] what the neighbours export to me
+    int *h_counts = nullptr;             // pinned, 4 ints
+    DevBuf<double> body_buf;
+    long long exchanged_bytes = 0;       // NVLink traffic of the steps since reset (both directions, this rank)
+  } slab;
 
   // SM-local scheduling of the gather kernels (dfr_kernels.cuh: VSched)
   DevBuf<unsigned int> sched_ctr;
@@ -347,11 +369,18 @@ int build_dyn_grid(dfr_context *c) {
   return DFR_OK;
 }
 
+int build_neighbor_lists(dfr_context *c);
+int slab_exchange_and_sort(dfr_context *c);
 // CompactNSearch replacement: counting sort of the fluid into cell order + neighbour lists
 int build_neighbors(dfr_context *c) {
   const int nc = c->P.grid.ncells;
   const int n = c->launch_nf;
   const int *nf_ptr = &c->dSt.p->nf;
+  if (c->slab.on) {
+    int rc = slab_exchange_and_sort(c);
+    if (rc) return rc;
+    return build_neighbor_lists(c);
+  }
   const int a = c->cur, b = 1 - c->cur;
   cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
   LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->P, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
@@ -364,7 +393,13 @@ int build_neighbors(dfr_context *c) {
          c->pid[b].p, c->pstate[b].p);
   c->cur = b;
   c->vcur = 1 - c->vcur;
-  rc = build_dyn_grid(c);
+  return build_neighbor_lists(c);
+}
+
+// neighbour lists of the sorted fluid (and the dynamic-boundary -> fluid rows)
+int build_neighbor_lists(dfr_context *c) {
+  const int n = c->launch_nf;
+  int rc = build_dyn_grid(c);
   if (rc) return rc;
   PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
@@ -390,11 +425,201 @@ int compute_boundary_volumes(dfr_context *c) {
 int sync_state(dfr_context *c) {
   CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->hSt->error_flags & 16) return fail(c, DFR_ERR_STATE, "slab: a particle moved further than one ghost layer in one step");
+  if (c->hSt->error_flags & 8) return fail(c, DFR_ERR_CAPACITY, "slab: export buffer too small");
   if (c->hSt->error_flags) {
     char buf[160];
     std::snprintf(buf, sizeof(buf), "neighbour list capacity exceeded (flags %d; longest rows f=%u b=%u, d entries=%u; cap f=%d b=%d d=%u)",
                   c->hSt->error_flags, c->hSt->list_used_f, c->hSt->list_used_b, c->hSt->list_used_d, c->cap_f, c->cap_b, c->cap_d);
     return fail(c, DFR_ERR_CAPACITY, buf);
+  }
+  return DFR_OK;
+}
+
+// ---- NCCL, loaded at run time (libnccl.so.2: the copy torch already mapped, else the system one) ----
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api(std::string *why) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) {
+      bool ok = true;
+      auto sym = [&](const char *name) {
+        void *p = dlsym(api.handle, name);
+        if (!p) ok = false;
+        return p;
+      };
+      api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+      api.Send = (decltype(api.Send))sym("ncclSend");
+      api.Recv = (decltype(api.Recv))sym("ncclRecv");
+      api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+      api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+      api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+      if (!ok) {
+        dlclose(api.handle);
+        api.handle = nullptr;
+      }
+    }
+  }
+  if (!api.handle) {
+    if (why) *why = "libnccl.so.2 could not be loaded (slab decomposition needs NCCL)";
+    return nullptr;
+  }
+  return &api;
+}
+#define NC(call)                                                                                                   \
+  do {                                                                                                             \
+    ncclResult_t r__ = (call);                                                                                     \
+    if (r__ != ncclSuccess) return fail(c, DFR_ERR_CUDA, std::string(#call) + ": " + nccl_api(nullptr)->GetErrorString(r__)); \
+  } while (0)
+
+// ghost update of one per-particle array (element size `esz` bytes): my boundary layers -> the neighbours' ghost layers
+int slab_sync(dfr_context *c, void *buf, size_t esz) {
+  auto &S = c->slab;
+  NcclApi *N = nccl_api(nullptr);
+  const int own_begin = S.h_ranges[0], own_end = S.h_ranges[1], bl_lo_end = S.h_ranges[2], bl_hi_begin = S.h_ranges[3], nf = S.h_ranges[4];
+  char *b = (char *)buf;
+  NC(N->GroupStart());
+  if (S.G.has_lo) {
+    NC(N->Send(b + (size_t)own_begin * esz, (size_t)(bl_lo_end - own_begin) * esz, ncclChar, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(b, (size_t)own_begin * esz, ncclChar, S.rank - 1, S.comm, c->stream));
+    S.exchanged_bytes += (long long)((bl_lo_end - own_begin) + own_begin) * (long long)esz;
+  }
+  if (S.G.has_hi) {
+    NC(N->Send(b + (size_t)bl_hi_begin * esz, (size_t)(own_end - bl_hi_begin) * esz, ncclChar, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(b + (size_t)own_end * esz, (size_t)(nf - own_end) * esz, ncclChar, S.rank + 1, S.comm, c->stream));
+    S.exchanged_bytes += (long long)((own_end - bl_hi_begin) + (nf - own_end)) * (long long)esz;
+  }
+  NC(N->GroupEnd());
+  c->launches++;
+  return DFR_OK;
+}
+int slab_allreduce(dfr_context *c, void *buf, size_t count, ncclDataType_t type, ncclRedOp_t op) {
+  NcclApi *N = nccl_api(nullptr);
+  NC(N->AllReduce(buf, buf, count, type, op, c->slab.comm, c->stream));
+  c->launches++;
+  return DFR_OK;
+}
+#define SLAB_SYNC(c, buf, esz)                    \
+  do {                                            \
+    if ((c)->slab.on) {                           \
+      int rc__ = slab_sync((c), (buf), (esz));    \
+      if (rc__) return rc__;                      \
+    }                                             \
+  } while (0)
+
+// Step start in slab mode: export the particles that now sit in my boundary layers (or beyond: emigrants), import the
+// neighbours', and re-sort.  Replaces the head of build_neighbors.
+int slab_exchange_and_sort(dfr_context *c) {
+  auto &S = c->slab;
+  NcclApi *N = nccl_api(nullptr);
+  const int a = c->cur, b = 1 - c->cur;
+  const int own_begin = S.h_ranges[0], own_end = S.h_ranges[1];
+  const int n_own = own_end - own_begin;
+  CU(cudaMemsetAsync(S.counts.p, 0, 4 * sizeof(int), c->stream));
+  LAUNCH(c, k_slab_select, cdiv(n_own, 128), 128, c->P, S.G, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p,
+         c->pid[a].p, c->pstate[a].p, S.send_cap, S.s_pos[0].p, S.s_vel[0].p, S.s_misc[0].p, S.s_pos[1].p, S.s_vel[1].p, S.s_misc[1].p,
+         S.counts.p, &c->dSt.p->error_flags);
+  // counts: mine to the host, and to the neighbours
+  NC(N->GroupStart());
+  if (S.G.has_lo) {
+    NC(N->Send(S.counts.p + 0, 1, ncclInt, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(S.counts.p + 2, 1, ncclInt, S.rank - 1, S.comm, c->stream));
+  }
+  if (S.G.has_hi) {
+    NC(N->Send(S.counts.p + 1, 1, ncclInt, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(S.counts.p + 3, 1, ncclInt, S.rank + 1, S.comm, c->stream));
+  }
+  NC(N->GroupEnd());
+  CU(cudaMemcpyAsync(S.h_counts, S.counts.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int send_lo = S.G.has_lo ? S.h_counts[0] : 0, send_hi = S.G.has_hi ? S.h_counts[1] : 0;
+  const int recv_lo = S.G.has_lo ? S.h_counts[2] : 0, recv_hi = S.G.has_hi ? S.h_counts[3] : 0;
+  if (send_lo > S.send_cap || send_hi > S.send_cap || recv_lo > S.send_cap || recv_hi > S.send_cap)
+    return fail(c, DFR_ERR_CAPACITY, "slab exchange buffer too small");
+  if ((int64_t)own_end + recv_lo + recv_hi > c->nf_cap) return fail(c, DFR_ERR_CAPACITY, "slab: local particle capacity exceeded");
+  // payload: positions and velocities straight behind my owned range, (kappa, kappa_v, id, state) through a scratch buffer
+  double4 *pos = c->pos[a].p, *vel = c->vel[c->vcur].p;
+  NC(N->GroupStart());
+  if (S.G.has_lo) {
+    NC(N->Send(S.s_pos[0].p, (size_t)send_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+    NC(N->Send(S.s_vel[0].p, (size_t)send_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+    NC(N->Send(S.s_misc[0].p, (size_t)send_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(pos + own_end, (size_t)recv_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(vel + own_end, (size_t)recv_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(S.r_misc.p, (size_t)recv_lo * 4, ncclDouble, S.rank - 1, S.comm, c->stream));
+  }
+  if (S.G.has_hi) {
+    NC(N->Send(S.s_pos[1].p, (size_t)send_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+    NC(N->Send(S.s_vel[1].p, (size_t)send_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+    NC(N->Send(S.s_misc[1].p, (size_t)send_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(pos + own_end + recv_lo, (size_t)recv_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(vel + own_end + recv_lo, (size_t)recv_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(S.r_misc.p + recv_lo, (size_t)recv_hi * 4, ncclDouble, S.rank + 1, S.comm, c->stream));
+  }
+  NC(N->GroupEnd());
+  c->launches++;
+  S.exchanged_bytes += (long long)(send_lo + send_hi + recv_lo + recv_hi) * 96;
+  const int n_recv = recv_lo + recv_hi;
+  LAUNCH(c, k_slab_unpack, cdiv(n_recv, 128), 128, S.r_misc.p, n_recv, own_end, c->kappa[a].p, c->kappav[a].p, c->pid[a].p, c->pstate[a].p);
+  // sort [own_begin, own_end + n_recv) by (cell, id) into the other buffers
+  const int n_src = n_own + n_recv;
+  const int nc = c->P.grid.ncells;
+  c->launch_nf = n_src;
+  LAUNCH(c, k_slab_set_nf, 1, 32, c->dSt.p, n_src);
+  CU(cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->stream));
+  LAUNCH(c, k_bin_count, cdiv(n_src, 128), 128, c->P, pos + own_begin, (const int *)nullptr, n_src, c->cell_start_f.p, c->cell_of_p.p,
+         c->rank_in_cell.p);
+  int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
+  if (rc) return rc;
+  LAUNCH(c, k_bin_scatter, cdiv(n_src, 128), 128, (const int *)nullptr, n_src, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
+         c->sorted_src_f.p);
+  LAUNCH(c, k_bin_sort_cells_by_id, cdiv(nc, 128), 128, c->cell_start_f.p, nc, c->sorted_src_f.p, c->pid[a].p + own_begin);
+  LAUNCH(c, k_permute_fluid, cdiv(n_src, 128), 128, c->dSt.p, c->sorted_src_f.p, pos + own_begin, vel + own_begin, c->kappa[a].p + own_begin,
+         c->kappav[a].p + own_begin, c->pid[a].p + own_begin, c->pstate[a].p + own_begin, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p,
+         c->kappav[b].p, c->pid[b].p, c->pstate[b].p);
+  c->cur = b;
+  c->vcur = 1 - c->vcur;
+  LAUNCH(c, k_slab_ranges, 1, 32, c->P, S.G, c->dSt.p, c->cell_start_f.p);
+  // both sides of a plane must agree on the shared layers before any ghost update is posted (a mismatched send/recv
+  // pair would hang): tell the neighbours how many particles my boundary layers hold, compare with my ghost layers
+  NC(N->GroupStart());
+  if (S.G.has_lo) {
+    NC(N->Send(&c->dSt.p->slab_ranges[5], 1, ncclInt, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(S.counts.p + 2, 1, ncclInt, S.rank - 1, S.comm, c->stream));
+  }
+  if (S.G.has_hi) {
+    NC(N->Send(&c->dSt.p->slab_ranges[6], 1, ncclInt, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(S.counts.p + 3, 1, ncclInt, S.rank + 1, S.comm, c->stream));
+  }
+  NC(N->GroupEnd());
+  CU(cudaMemcpyAsync(S.h_counts, S.counts.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  rc = sync_state(c);
+  if (rc) return rc;
+  std::memcpy(S.h_ranges, c->hSt->slab_ranges, sizeof(S.h_ranges));
+  const int ghost_lo = S.h_ranges[0], ghost_hi = S.h_ranges[4] - S.h_ranges[1];
+  if ((S.G.has_lo && S.h_counts[2] != ghost_lo) || (S.G.has_hi && S.h_counts[3] != ghost_hi)) {
+    char buf[200];
+    std::snprintf(buf, sizeof(buf), "slab %d: ghost layers (%d, %d) do not match the neighbours' boundary layers (%d, %d)", S.rank, ghost_lo,
+                  ghost_hi, S.G.has_lo ? S.h_counts[2] : 0, S.G.has_hi ? S.h_counts[3] : 0);
+    return fail(c, DFR_ERR_STATE, buf);
   }
   return DFR_OK;
 }
@@ -437,10 +662,13 @@ int launch_solver(dfr_context *c) {
 #define PUSH_ARGS c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0
   if (warm) {
     PLAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, RHO_ARGS);
+    SLAB_SYNC(c, c->xk.p, sizeof(double4));
     launch_boundary_side<PRESSURE>(c, false, 0);
     PLAUNCH(c, (k_push<PRESSURE, false>), g, PUSH_ARGS);
+    SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
   }
   PLAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, RHO_ARGS);
+  SLAB_SYNC(c, c->xk.p, sizeof(double4));
   const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
   int launched = 0;
   int spec = PRESSURE ? c->spec_prs : c->spec_div;
@@ -451,7 +679,14 @@ int launch_solver(dfr_context *c) {
       c->prof_iter = launched + it;
       launch_boundary_side<PRESSURE>(c, true, 1);
       PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
+      SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
       PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
+      if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
+        int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
+        if (rc) return rc;
+        LAUNCH(c, k_solver_decide<PRESSURE>, 1, 32, c->P, c->dSt.p);
+        SLAB_SYNC(c, c->xk.p, sizeof(double4));
+      }
     }
     c->prof_solver = -1;
     launched += spec;
@@ -545,7 +780,7 @@ int contact_rest_state(dfr_context *c) {
 
 // one SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169)
 int launch_step(dfr_context *c) {
-  const int n = c->launch_nf, g = cdiv(n, 128);
+  int n = c->launch_nf, g = cdiv(n, 128);
   if (c->cfg.use_rigid_contact_solver) {  // TimeStepDiffDFSPH::performNeighborhoodSearch (:2044-2056): z-sort every 500 steps
     if (c->sort_counter % 500 == 0) {
       int rc = contact_sort_current(c);
@@ -556,9 +791,12 @@ int launch_step(dfr_context *c) {
   LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p);
   int rc = build_neighbors(c);
   if (rc) return rc;
+  n = c->launch_nf;  // slab mode: the number of local particles changes with every exchange
+  g = cdiv(n, 128);
   int a = c->cur;
   PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
          c->sgp.p, c->xrho.p);
+  SLAB_SYNC(c, c->xrho.p, sizeof(double4));
   bool scale_kv = false;
   if (c->cfg.enable_divergence_solver) {
     rc = launch_solver<false>(c);
@@ -566,11 +804,19 @@ int launch_step(dfr_context *c) {
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
   if (c->cfg.surface_tension_method == 2)
+  {
     PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
+    SLAB_SYNC(c, c->normal.p, sizeof(double4));
+  }
   PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
          c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
   c->vcur = 1 - c->vcur;
+  SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
+  if (c->slab.on) {  // max |v + a h|^2 over all slabs (ordered bits of positive doubles)
+    rc = slab_allreduce(c, &c->dSt.p->cfl_max_bits, 1, ncclUint64, ncclMax);
+    if (rc) return rc;
+  }
   LAUNCH(c, k_cfl_finish, 1, 32, c->P, c->dSt.p);
   rc = launch_solver<true>(c);
   if (rc) return rc;
@@ -585,7 +831,13 @@ int launch_step(dfr_context *c) {
     }
   }
   if (c->P.n_bodies > 0) {
-    LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
+    if (c->slab.on) {  // per-body force / torque / Jacobian rows: sum over the slabs, then every rank advances the bodies alike
+      LAUNCH(c, k_body_rows_to_buf, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p, c->slab.body_buf.p);
+      rc = slab_allreduce(c, c->slab.body_buf.p, (size_t)c->P.n_bodies * ACC_N, ncclDouble, ncclSum);
+      if (rc) return rc;
+      LAUNCH(c, k_body_buf_apply, c->P.n_bodies, 32, c->dBodies.p, c->slab.body_buf.p);
+    } else
+      LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
     if (c->cfg.use_rigid_contact_solver) {
       LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_PRE);
       if (c->n_dyn_p > 0) {
@@ -626,7 +878,7 @@ int reset_device_state(dfr_context *c) {
     c->sort_counter = 0;
   }
   // fluid: initial state back into the current buffers (id order)
-  const size_t n = (size_t)c->nf0;
+  const size_t n = (size_t)c->nf_loc0;
   c->cur = 0;
   c->vcur = 0;
   if (n) {
@@ -636,6 +888,7 @@ int reset_device_state(dfr_context *c) {
     CU(cudaMemcpyAsync(c->kappav[0].p, c->kappav_init.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     std::vector<int> ids(c->nf_cap);
     for (int64_t i = 0; i < c->nf_cap; i++) ids[i] = (int)i;
+    if (c->slab.on) std::copy(c->h_ids0.begin(), c->h_ids0.end(), ids.begin());
     CU(cudaMemcpyAsync(c->pid[0].p, ids.data(), c->nf_cap * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemsetAsync(c->pstate[0].p, 0, c->nf_cap * sizeof(int), c->stream));
@@ -669,7 +922,15 @@ int reset_device_state(dfr_context *c) {
   std::memset(&st, 0, sizeof(st));
   st.h = c->cfg.time_step_size;
   st.h_step = st.h;
-  st.nf = (int)c->nf0;
+  st.nf = (int)c->nf_loc0;
+  st.own_begin = 0;
+  st.own_end = st.nf;
+  if (c->slab.on) {
+    c->slab.h_ranges[0] = 0;
+    c->slab.h_ranges[1] = c->slab.h_ranges[2] = c->slab.h_ranges[3] = c->slab.h_ranges[4] = st.nf;
+    c->slab.exchanged_bytes = 0;
+    c->launch_nf = st.nf;
+  }
   CU(cudaMemcpyAsync(c->dSt.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *c->hSt = st;
@@ -775,6 +1036,10 @@ void dfr_destroy(dfr_context *c) {
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
   c->sched_ctr.free();
+  for (int k = 0; k < 2; k++) { c->slab.s_pos[k].free(); c->slab.s_vel[k].free(); c->slab.s_misc[k].free(); }
+  c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free();
+  if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
+  if (c->slab.comm && nccl_api(nullptr)) nccl_api(nullptr)->CommDestroy(c->slab.comm);
   c->c_vol0.free(); c->c_dens0.free(); c->c_dens.free(); c->c_records.free(); c->c_vel.free(); c->c_order.free();
   for (auto &p : c->prof_pending) {
     cudaEventDestroy(p.e0);
@@ -854,6 +1119,47 @@ int dfr_add_emitter(dfr_context *c, int width, int height, const double position
   e.next_emit_time = emit_start;
   e.emit_counter = 0;
   c->h_emitters.push_back(e);
+  return DFR_OK;
+}
+
+int dfr_slab_unique_id(char out[DFR_SLAB_ID_BYTES]) {
+  std::string why;
+  NcclApi *N = nccl_api(&why);
+  if (!N || !out) return DFR_ERR_INVALID;
+  static_assert(sizeof(ncclUniqueId) <= DFR_SLAB_ID_BYTES, "ncclUniqueId grew");
+  ncclUniqueId id;
+  if (N->GetUniqueId(&id) != ncclSuccess) return DFR_ERR_CUDA;
+  std::memset(out, 0, DFR_SLAB_ID_BYTES);
+  std::memcpy(out, &id, sizeof(id));
+  return DFR_OK;
+}
+
+int dfr_slab_configure(dfr_context *c, int rank, int n_ranks, const char id_bytes[DFR_SLAB_ID_BYTES]) {
+  if (!c) return DFR_ERR_INVALID;
+  if (c->finalized) return fail(c, DFR_ERR_STATE, "slab_configure after finalize");
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id_bytes) return fail(c, DFR_ERR_INVALID, "bad slab rank");
+  if (n_ranks == 1) return DFR_OK;  // one slab is the plain context
+  std::string why;
+  NcclApi *N = nccl_api(&why);
+  if (!N) return fail(c, DFR_ERR_INVALID, why);
+  cudaSetDevice(c->device);
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  NC(N->CommInitRank(&c->slab.comm, n_ranks, id, rank));
+  c->slab.on = true;
+  c->slab.rank = rank;
+  c->slab.n = n_ranks;
+  return DFR_OK;
+}
+
+int dfr_slab_info(dfr_context *c, int64_t out[4]) {
+  if (!c || !c->finalized || !out) return fail(c, DFR_ERR_STATE, "not finalized");
+  int rc = sync_state(c);
+  if (rc) return rc;
+  out[0] = c->hSt->own_end - c->hSt->own_begin;
+  out[1] = c->hSt->nf - out[0];
+  out[2] = c->slab.exchanged_bytes;
+  out[3] = c->slab.on ? c->slab.n : 1;
   return DFR_OK;
 }
 
@@ -969,10 +1275,82 @@ int dfr_finalize(dfr_context *c) {
   P.grid.inv_cell = 1.0 / cell;
   P.grid.ncells = P.grid.nx * P.grid.ny * P.grid.nz;
 
+  // ---- slab decomposition: cut the z layers into ranges of equal particle count, keep my range (+ pad) ----
+  c->nf_loc0 = c->nf0;
+  int slab_ghost_estimate = 0;
+  P.n_global = c->nf0;
+  if (c->slab.on) {
+    if (!c->h_emitters.empty()) return fail(c, DFR_ERR_INVALID, "slab decomposition: emitters are not supported");
+    if (cfg.use_rigid_contact_solver) return fail(c, DFR_ERR_INVALID, "slab decomposition: the rigid contact solver is not supported");
+    auto &S = c->slab;
+    GridGeom &G = P.grid;
+    std::vector<int64_t> hist(G.nz, 0);
+    std::vector<int> zc(c->nf0);
+    for (int64_t i = 0; i < c->nf0; i++) {
+      int z = (int)std::floor((c->h_fx[3 * i + 2] - G.oz) * G.inv_cell);
+      z = std::min(std::max(z, 0), G.nz - 1);
+      zc[i] = z;
+      hist[z]++;
+    }
+    std::vector<int> planes(S.n + 1, 0);
+    planes[S.n] = G.nz;
+    int64_t cum = 0;
+    int k = 1;
+    for (int z = 0; z < G.nz && k < S.n; z++) {
+      cum += hist[z];
+      while (k < S.n && cum >= (c->nf0 * (int64_t)k) / S.n) planes[k++] = z + 1;
+    }
+    for (int r = 0; r < S.n; r++)
+      if (planes[r + 1] - planes[r] < 2 * G.reach + 1)
+        return fail(c, DFR_ERR_INVALID, "slab decomposition: a slab would be thinner than two support radii (too many ranks for this scene)");
+    const int zlo = planes[S.rank], zhi = planes[S.rank + 1];
+    const int pad = 2 * G.reach + 2;
+    S.G.reach = G.reach;
+    S.G.has_lo = S.rank > 0;
+    S.G.has_hi = S.rank < S.n - 1;
+    S.G.own_zlo = pad;
+    S.G.own_zhi = pad + (zhi - zlo);
+    // particles per exchanged layer set (reach + 1 layers on either side of either plane), for the buffer sizes
+    int64_t est = 0;
+    auto layers = [&](int z0, int z1) {
+      int64_t s2 = 0;
+      for (int z = std::max(z0, 0); z < std::min(z1, G.nz); z++) s2 += hist[z];
+      est = std::max(est, s2);
+    };
+    layers(zlo - G.reach - 1, zlo);
+    layers(zlo, zlo + G.reach + 1);
+    layers(zhi - G.reach - 1, zhi);
+    layers(zhi, zhi + G.reach + 1);
+    slab_ghost_estimate = (int)est;
+    G.z_shift = zlo - pad;
+    G.nz = (zhi - zlo) + 2 * pad;
+    G.ncells = G.nx * G.ny * G.nz;
+    c->h_ids0.clear();
+    for (int64_t i = 0; i < c->nf0; i++)
+      if (zc[i] >= zlo && zc[i] < zhi) c->h_ids0.push_back((int)i);
+    c->nf_loc0 = (int64_t)c->h_ids0.size();
+    P.slab = 1;
+  }
+
   // ---- allocations ----
   c->nf_cap = c->nf0 + std::max(0, cfg.max_emitted_particles);
+  if (c->slab.on) {
+    // room for the flow to pile up in my slab (x1.5) and for two ghost layers
+    c->nf_cap = c->nf_loc0 + c->nf_loc0 / 2 + 4 * (int64_t)slab_ghost_estimate + 16384;
+    c->slab.send_cap = 3 * slab_ghost_estimate + 8192;
+  }
   const size_t N = (size_t)std::max<int64_t>(c->nf_cap, 1);
-  c->launch_nf = c->h_emitters.empty() ? (int)c->nf0 : (int)c->nf_cap;  // emitters grow st->nf on the device
+  c->launch_nf = c->h_emitters.empty() ? (int)c->nf_loc0 : (int)c->nf_cap;  // emitters grow st->nf on the device
+  if (c->slab.on) {
+    auto &S = c->slab;
+    for (int k = 0; k < 2; k++) {
+      CU(S.s_pos[k].alloc(S.send_cap)); CU(S.s_vel[k].alloc(S.send_cap)); CU(S.s_misc[k].alloc(S.send_cap));
+    }
+    CU(S.r_misc.alloc(2 * (size_t)S.send_cap));
+    CU(S.counts.alloc(4));
+    CU(S.body_buf.alloc(std::max<size_t>(c->bodies.size(), 1) * ACC_N));
+    if (cudaMallocHost((void **)&S.h_counts, 4 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
+  }
   CU(c->dEmitters.alloc(std::max<size_t>(c->h_emitters.size(), 1)));
   const int nc = P.grid.ncells;
   CU(c->dSt.alloc(1));
@@ -1034,14 +1412,15 @@ int dfr_finalize(dfr_context *c) {
   }
 
   // ---- uploads ----
-  if (c->nf0) {
-    std::vector<double4> p4(c->nf0), v4(c->nf0);
-    for (int64_t i = 0; i < c->nf0; i++) {
-      p4[i] = make_double4(c->h_fx[3 * i], c->h_fx[3 * i + 1], c->h_fx[3 * i + 2], 0.0);
-      v4[i] = make_double4(c->h_fv[3 * i], c->h_fv[3 * i + 1], c->h_fv[3 * i + 2], 0.0);
+  if (c->nf_loc0) {
+    std::vector<double4> p4(c->nf_loc0), v4(c->nf_loc0);
+    for (int64_t k = 0; k < c->nf_loc0; k++) {
+      const int64_t i = c->slab.on ? c->h_ids0[k] : k;
+      p4[k] = make_double4(c->h_fx[3 * i], c->h_fx[3 * i + 1], c->h_fx[3 * i + 2], 0.0);
+      v4[k] = make_double4(c->h_fv[3 * i], c->h_fv[3 * i + 1], c->h_fv[3 * i + 2], 0.0);
     }
-    CU(cudaMemcpy(c->pos_init.p, p4.data(), c->nf0 * sizeof(double4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->vel_init.p, v4.data(), c->nf0 * sizeof(double4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->pos_init.p, p4.data(), c->nf_loc0 * sizeof(double4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->vel_init.p, v4.data(), c->nf_loc0 * sizeof(double4), cudaMemcpyHostToDevice));
   }
   if (c->n_b) {
     CU(cudaMemcpy(c->bpos.p, h_bpos.data(), c->n_b * sizeof(double4), cudaMemcpyHostToDevice));
@@ -1085,18 +1464,26 @@ int dfr_finalize(dfr_context *c) {
 int dfr_load_fluid_state(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
-  const int64_t n = c->nf0;
+  const int64_t n = c->nf_loc0;  // arrays are indexed by particle id; a slab keeps the ids it owned at t = 0
+  auto id_of = [&](int64_t k) { return c->slab.on ? (int64_t)c->h_ids0[k] : k; };
   std::vector<double4> tmp(n);
+  std::vector<double> tmp1(n);
   if (x) {
-    for (int64_t i = 0; i < n; i++) tmp[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.0);
+    for (int64_t k = 0; k < n; k++) tmp[k] = make_double4(x[3 * id_of(k)], x[3 * id_of(k) + 1], x[3 * id_of(k) + 2], 0.0);
     CU(cudaMemcpy(c->pos_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
   }
   if (v) {
-    for (int64_t i = 0; i < n; i++) tmp[i] = make_double4(v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
+    for (int64_t k = 0; k < n; k++) tmp[k] = make_double4(v[3 * id_of(k)], v[3 * id_of(k) + 1], v[3 * id_of(k) + 2], 0.0);
     CU(cudaMemcpy(c->vel_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
   }
-  if (kappa) CU(cudaMemcpy(c->kappa_init.p, kappa, n * sizeof(double), cudaMemcpyHostToDevice));
-  if (kappa_v) CU(cudaMemcpy(c->kappav_init.p, kappa_v, n * sizeof(double), cudaMemcpyHostToDevice));
+  if (kappa) {
+    for (int64_t k = 0; k < n; k++) tmp1[k] = kappa[id_of(k)];
+    CU(cudaMemcpy(c->kappa_init.p, tmp1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (kappa_v) {
+    for (int64_t k = 0; k < n; k++) tmp1[k] = kappa_v[id_of(k)];
+    CU(cudaMemcpy(c->kappav_init.p, tmp1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  }
   // like the oracle, loading re-bases the running state: positions/velocities/kappas are replaced in id order
   return reset_device_state(c);
 }
@@ -1181,7 +1568,7 @@ int dfr_get_step_info(dfr_context *c, dfr_step_info *info) {
   info->iterations_v = s.last_iters_v;
   info->step_count = s.step_count;
   info->trajectory_finished = s.finished;
-  info->num_fluid_particles = s.nf;
+  info->num_fluid_particles = c->slab.on ? (int64_t)(s.own_end - s.own_begin) : (int64_t)s.nf;  // slab mode: owned by this rank
   info->total_pressure_iterations = s.total_iters;
   info->total_divergence_iterations = s.total_iters_v;
   info->total_particle_steps = s.total_particle_steps;
@@ -1301,7 +1688,7 @@ int64_t dfr_num_fluid(dfr_context *c) {
   if (!c || !c->finalized) return c ? c->nf0 : 0;
   cudaSetDevice(c->device);
   if (sync_state(c)) return 0;
-  return c->hSt->nf;
+  return c->slab.on ? c->nf0 : c->hSt->nf;  // arrays of the parity dumps are indexed by the scene's particle ids
 }
 int64_t dfr_num_body_particles(dfr_context *c, int body) {
   return (c && body >= 0 && body < (int)c->bodies.size()) ? c->bodies[body].n : 0;
@@ -1313,10 +1700,12 @@ int dfr_download_fluid(dfr_context *c, int field, double *out) {
   cudaSetDevice(c->device);
   int rc = sync_state(c);
   if (rc) return rc;
-  const int n = c->hSt->nf;
-  if (n == 0) return DFR_OK;
+  // slab mode: only the particles this rank owns are written (entries of other ids stay untouched; the caller merges)
+  const int i0 = c->hSt->own_begin;
+  const int n = c->hSt->own_end - i0;
+  if (n <= 0) return DFR_OK;
   std::vector<int> ids(n);
-  CU(cudaMemcpy(ids.data(), c->pid[c->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ids.data(), c->pid[c->cur].p + i0, n * sizeof(int), cudaMemcpyDeviceToHost));
   const double4 *v4 = nullptr;
   const double *s1 = nullptr;
   switch (field) {
@@ -1334,14 +1723,14 @@ int dfr_download_fluid(dfr_context *c, int field, double *out) {
   }
   if (v4) {
     std::vector<double4> t(n);
-    CU(cudaMemcpy(t.data(), v4, n * sizeof(double4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t.data(), v4 + i0, n * sizeof(double4), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
       double *o = out + 3 * (size_t)ids[i];
       o[0] = t[i].x; o[1] = t[i].y; o[2] = t[i].z;
     }
   } else {
     std::vector<double> t(n);
-    CU(cudaMemcpy(t.data(), s1, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t.data(), s1 + i0, n * sizeof(double), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) out[ids[i]] = t[i];
   }
   return DFR_OK;
@@ -1391,6 +1780,7 @@ int dfr_get_neighbors(dfr_context *c, int set_a, int set_b, int32_t *counts, int
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   const int nb = (int)c->bodies.size();
   if (set_a < -1 || set_a >= nb || set_b < -1 || set_b >= nb) return fail(c, DFR_ERR_INVALID, "bad set index");
+  if (c->slab.on) return fail(c, DFR_ERR_INVALID, "neighbour dumps are not available on a slab-decomposed context");
   cudaSetDevice(c->device);
   // the same neighbourhood build the step runs, on the current positions
   int rc = build_neighbors(c);

@@ -125,7 +125,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 __device__ __forceinline__ void cell_of(const GridGeom &g, double x, double y, double z, int &cx, int &cy, int &cz) {
   cx = clampi((int)floor((x - g.ox) * g.inv_cell), 0, g.nx - 1);
   cy = clampi((int)floor((y - g.oy) * g.inv_cell), 0, g.ny - 1);
-  cz = clampi((int)floor((z - g.oz) * g.inv_cell), 0, g.nz - 1);
+  cz = clampi((int)floor((z - g.oz) * g.inv_cell) - g.z_shift, 0, g.nz - 1);
 }
 __device__ __forceinline__ int cell_lin(const GridGeom &g, int cx, int cy, int cz) { return (cz * g.ny + cy) * g.nx + cx; }
 
@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
   int cf = 0, cb = 0;
-  if (i < n) {
+  (void)n;
+  if (i >= st->own_begin && i < st->own_end) {
     const int lane = i & 31;
     const double4 p = pos[i];
     (void)lane;
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
-  if (i >= st->nf) continue;
+  if (i < st->own_begin || i >= st->own_end) continue;
   const double4 pi = pos[i];
   double dens = P.volume * P.W_zero;
   double S = 0.0;
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
   const int i = vb_ * 128 + threadIdx.x;
   const double h = PRESSURE ? st->h : st->h_step;
   double err = 0.0;
-  if (i < nf) {
+  if (i >= st->own_begin && i < st->own_end) {
     const double4 pi = pos[i];
     const double4 vi = vel[i];
       double delta = 0.0;
@@ -703,7 +704,10 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
       }
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0 && P.slab) {  // the stopping rule needs the sum over all slabs: k_solver_decide applies it
+        st->res_sum = red[0];
+        st->ticket = 0;
+      } else if (threadIdx.x == 0) {
         const double avg = red[0] / (double)nf;
         st->last_residual = avg;
         st->ticket = 0;
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
   }
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
-  if (i >= st->nf) continue;
+  if (i < st->own_begin || i >= st->own_end) continue;
   if (state[i] != 0) continue;
   const double h = PRESSURE ? st->h : st->h_step;
   const double4 pi = xk[i];
@@ -821,6 +825,7 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_co
     }
     for (int p = s + lane; p < e; p += 32) {
       const int i = idx_d[p];
+      if (i < st->own_begin || i >= st->own_end) continue;  // ghosts are summed by the slab that owns them
       const double4 pi = ldg4(xk + i);
       const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
       // real reaction force of the push that follows: F = -m dv / dt = m k_i g, g = -V_j gradW
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
-  if (i >= st->nf) continue;
+  if (i < st->own_begin || i >= st->own_end) continue;
   const double4 pi = xrho[i];
   d3 n = mk3(0, 0, 0);
   for_neighbors4(
@@ -1011,7 +1016,8 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
   double mag = 0.0;
-  if (i < nf) {
+  (void)nf;
+  if (i >= st->own_begin && i < st->own_end) {
     const double4 pi = xrho[i];
     const double4 vi = vel[i];
     d3 a = mk3(P.gx, P.gy, P.gz);

@@ -16,6 +16,10 @@ __global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, Bo
     st->div_iters = 0;
     st->ticket = 0;
     st->cfl_max_bits = 0ull;
+    if (!P.slab) {  // one context holds everything (emitters may have grown nf at the end of the last step)
+      st->own_begin = 0;
+      st->own_end = st->nf;
+    }
   }
   if (b < P.n_bodies) {
     BodyDev &B = bodies[b];
@@ -306,7 +310,7 @@ __global__ void k_body_update(const __grid_constant__ Params P, StepState *st, B
   if (b == 0 && phase != BODY_POST) {
     st->last_iters = st->prs_iters;
     st->total_iters += st->prs_iters;
-    st->total_particle_steps += st->nf;
+    st->total_particle_steps += st->own_end - st->own_begin;
     st->time += st->h_step;
     st->finished = (st->time >= P.target_time + P.uniform_acc_time) ? 1 : 0;
   }

@@ -1,0 +1,181 @@
+// Slab domain decomposition of one large scene over several GPUs (BASELINE.json configs[4]).
+// The reference has nothing like it (one process, OpenMP); what must be preserved is the result of the
+// single-domain step, up to summation order.
+//
+// Decomposition: the cell index is x-fastest / z-slowest, so a range of z cell layers is a contiguous range of
+// the cell-sorted particle arrays.  Rank r owns the layers [own_zlo, own_zhi) of its local grid; one support
+// radius (`reach` layers) on each side is the boundary layer it exports / the ghost layer it imports:
+//
+//     sorted arrays of rank r:   [ ghost_lo | bl_lo ... interior ... bl_hi | ghost_hi ]
+//                                            ^own_begin                    ^own_end
+//
+// Both neighbours sort the shared particles by (cell, particle id), so rank r's bl_hi range and rank r+1's
+// ghost_lo range hold the same particles in the same order: a ghost update of any per-particle array is one
+// contiguous send + one contiguous receive per side (NCCL over NVLink), no packing.
+// Per step (dfr_api.cu: slab_* functions): particles whose new position lies in an export layer - including the
+// ones that just crossed the plane - are sent with their full state; the receiver owns what falls into its layers
+// and keeps the rest as ghosts; the sender keeps its emigrants as ghosts for this step.  Then every kernel that
+// produces a gathered array (x|rho, x|k, v, n|rho) is followed by a ghost update of that array, residual sums, the
+// CFL maximum and the per-body force/torque/Jacobian rows are all-reduced, and the rigid bodies (replicated on every
+// rank) are advanced identically everywhere.
+#pragma once
+#include "dfr_kernels.cuh"
+
+namespace dfr {
+
+struct SlabGeom {
+  int own_zlo, own_zhi;  // owned z layers (local grid)
+  int has_lo, has_hi;    // neighbours exist
+  int reach;
+};
+
+// Particles of the owned range whose CURRENT position lies in an export layer are appended to the send buffers
+// (order irrelevant: the receiver sorts).  misc = (kappa, kappa_v, id, state).
+__global__ void k_slab_select(const __grid_constant__ Params P, const SlabGeom G, const StepState *st, const double4 *pos, const double4 *vel,
+                              const double *kappa, const double *kappav, const int *pid, const int *pstate, int capacity,
+                              double4 *out_pos_lo, double4 *out_vel_lo, double4 *out_misc_lo, double4 *out_pos_hi, double4 *out_vel_hi,
+                              double4 *out_misc_hi, int *counts /* [2], zeroed */, int *error_flags) {
+  const int i = st->own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->own_end) return;
+  const double4 p = pos[i];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const bool lo = G.has_lo && cz < G.own_zlo + G.reach;
+  const bool hi = G.has_hi && cz >= G.own_zhi - G.reach;
+  if (!lo && !hi) return;
+  const double4 m = make_double4(kappa[i], kappav[i], __longlong_as_double((long long)pid[i]), __longlong_as_double((long long)pstate[i]));
+  if (lo) {
+    const int k = atomicAdd(&counts[0], 1);
+    if (k < capacity) {
+      out_pos_lo[k] = p;
+      out_vel_lo[k] = vel[i];
+      out_misc_lo[k] = m;
+    } else
+      atomicOr(error_flags, 8);
+  }
+  if (hi) {
+    const int k = atomicAdd(&counts[1], 1);
+    if (k < capacity) {
+      out_pos_hi[k] = p;
+      out_vel_hi[k] = vel[i];
+      out_misc_hi[k] = m;
+    } else
+      atomicOr(error_flags, 8);
+  }
+}
+
+// received (kappa, kappa_v, id, state) records -> the persistent arrays, appended at `at`
+__global__ void k_slab_unpack(const double4 *misc, int n, int at, double *kappa, double *kappav, int *pid, int *pstate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double4 m = misc[k];
+  kappa[at + k] = m.x;
+  kappav[at + k] = m.y;
+  pid[at + k] = (int)__double_as_longlong(m.z);
+  pstate[at + k] = (int)__double_as_longlong(m.w);
+}
+
+__global__ void k_slab_set_nf(StepState *st, int nf) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) st->nf = nf;
+}
+
+// cells are sorted by source slot (k_bin_sort_cells); here by particle id, so that two ranks holding the same particles
+// in a cell order them identically
+__global__ void k_bin_sort_cells_by_id(const unsigned int *cell_start, int ncells, int *sorted_src, const int *pid_src) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int s = (int)cell_start[c], e = (int)cell_start[c + 1];
+  int *a = sorted_src + s;
+  for (int i = 1; i < e - s; i++) {  // insertion sort: cells hold a handful of particles
+    const int v = a[i];
+    const int kv = pid_src[v];
+    int j = i - 1;
+    while (j >= 0 && pid_src[a[j]] > kv) {
+      a[j + 1] = a[j];
+      j--;
+    }
+    a[j + 1] = v;
+  }
+}
+
+// owned / boundary-layer ranges of the freshly sorted arrays, from the cell table
+__global__ void k_slab_ranges(const __grid_constant__ Params P, const SlabGeom G, StepState *st, const unsigned int *cell_start) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int layer = P.grid.nx * P.grid.ny;
+  const int nf = st->nf;
+  const int own_begin = G.has_lo ? (int)cell_start[(size_t)G.own_zlo * layer] : 0;
+  const int own_end = G.has_hi ? (int)cell_start[(size_t)G.own_zhi * layer] : nf;
+  st->own_begin = own_begin;
+  st->own_end = own_end;
+  st->slab_ranges[0] = own_begin;
+  st->slab_ranges[1] = own_end;
+  st->slab_ranges[2] = G.has_lo ? (int)cell_start[(size_t)(G.own_zlo + G.reach) * layer] : own_begin;  // end of bl_lo
+  st->slab_ranges[3] = G.has_hi ? (int)cell_start[(size_t)(G.own_zhi - G.reach) * layer] : own_end;    // begin of bl_hi
+  st->slab_ranges[4] = nf;
+  st->slab_ranges[5] = st->slab_ranges[2] - own_begin;  // particles in my low / high boundary layer
+  st->slab_ranges[6] = own_end - st->slab_ranges[3];
+  // particles that escaped beyond the ghost layers cannot be handled (they would need more than one hop)
+  const int ghost_lo_begin = G.has_lo ? (int)cell_start[(size_t)(G.own_zlo - G.reach) * layer] : 0;
+  const int ghost_hi_end = G.has_hi ? (int)cell_start[(size_t)(G.own_zhi + G.reach) * layer] : nf;
+  if (ghost_lo_begin != 0 || ghost_hi_end != nf) atomicOr(&st->error_flags, 16);
+}
+
+// TimeStepDiffDFSPH::pressureSolve / divergenceSolve stopping rules (:711-743, :828-861) on the all-reduced residual
+template <bool PRESSURE>
+__global__ void k_solver_decide(const __grid_constant__ Params P, StepState *st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+  const double avg = st->res_sum / (double)P.n_global;
+  st->last_residual = avg;
+  if (PRESSURE) {
+    const double eta = P.max_error * 0.01 * P.density0;
+    const int it = st->prs_iters + 1;
+    st->prs_iters = it;
+    const bool chk = (avg <= eta);
+    if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
+  } else {
+    const double eta = (1.0 / st->h_step) * P.max_error_v * 0.01 * P.density0;
+    const int it = st->div_iters + 1;
+    st->div_iters = it;
+    const bool chk = (avg <= eta);
+    if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
+  }
+}
+
+// k_body_reduce split in two around the all-reduce of the per-body rows
+__global__ void k_body_rows_to_buf(const BodyDev *bodies, double *acc_rows, double *buf) {
+  const BodyDev &B = bodies[blockIdx.x];
+  for (int k = threadIdx.x; k < ACC_N; k += blockDim.x) {
+    double s = 0.0;
+    if (B.dynamic)
+      for (int r = 0; r < B.blk_count; r++) {
+        double *p = acc_rows + (size_t)(B.blk_begin + r) * ACC_N + k;
+        s += *p;
+        *p = 0.0;
+      }
+    buf[(size_t)blockIdx.x * ACC_N + k] = s;
+  }
+}
+__global__ void k_body_buf_apply(BodyDev *bodies, const double *buf) {
+  BodyDev &B = bodies[blockIdx.x];
+  if (!B.dynamic || threadIdx.x != 0) return;
+  const double *tot = buf + (size_t)blockIdx.x * ACC_N;
+  B.force += mk3(tot[ACC_F], tot[ACC_F + 1], tot[ACC_F + 2]);
+  B.torque += mk3(tot[ACC_T], tot[ACC_T + 1], tot[ACC_T + 2]);
+  if (!B.animated) {
+    for (int k = 0; k < 9; k++) {
+      B.net_f_v.a[k] = tot[ACC_FV + k];
+      B.net_f_x.a[k] = tot[ACC_FX + k];
+      B.net_f_w.a[k] = tot[ACC_FW + k];
+      B.net_t_v.a[k] = tot[ACC_TV + k];
+      B.net_t_x.a[k] = tot[ACC_TX + k];
+      B.net_t_w.a[k] = tot[ACC_TW + k];
+    }
+    for (int k = 0; k < 12; k++) {
+      B.net_f_q.a[k] = tot[ACC_FQ + k];
+      B.net_t_q.a[k] = tot[ACC_TQ + k];
+    }
+  }
+}
+
+}  // namespace dfr

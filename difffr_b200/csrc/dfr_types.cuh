@@ -16,6 +16,7 @@ struct GridGeom {
   int nx, ny, nz;
   int ncells;
   int reach;
+  int z_shift;  // slab decomposition: local z cell = global z cell - z_shift (global origin and arithmetic on every rank)
 };
 
 // Solver parameters that never change during a trajectory (constant for all kernels).
@@ -38,6 +39,8 @@ struct Params {
   double target_time, uniform_acc_time;
   double time_step_size0;
   int n_bodies, n_dyn_bodies;
+  int slab;                // slab-decomposed context: residual sums and body accumulators are all-reduced between kernels
+  long long n_global;      // fluid particles of the whole scene (slab mode)
 };
 
 // Mutable per-step scalars; lives in device memory so a step never needs the host.
@@ -46,7 +49,8 @@ struct StepState {
   double h_step;  // the "OLD" h captured at the top of step() (TimeStepDiffDFSPH.cpp:535)
   double time;
   unsigned long long cfl_max_bits;  // max |v + a h|^2 as ordered bits (all values > 0)
-  int nf;                           // active fluid particles
+  int nf;                           // active fluid particles held by this context (slab mode: owned + ghosts)
+  int own_begin, own_end;           // sorted range this context computes (everything unless slab-decomposed)
   int step_count;
   int finished;
   int div_active, div_iters;
@@ -58,6 +62,8 @@ struct StepState {
   long long nbr_entries_f, nbr_entries_b;   // of the current step (sum of counts)
   unsigned int list_used_f, list_used_b, list_used_d;
   double last_residual;
+  double res_sum;                   // slab mode: local residual sum of the iteration, all-reduced before the stopping rule
+  int slab_ranges[8];               // slab mode: own_begin, own_end, end of the low boundary layer, begin of the high one, nf
 };
 
 // Accumulator row written by the boundary-side kernel, per block: the eight net Jacobian blocks of

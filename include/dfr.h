@@ -113,6 +113,20 @@ int dfr_add_body(dfr_context *ctx, int64_t n, const double *x_local, int is_dyna
  * (DiffDFSPHModule.cpp:60-75; TimeStepDiffDFSPH.cpp:2087-2095). */
 int dfr_set_init_v_omega(dfr_context *ctx, int body, const double v0[3], const double omega0[3]);
 
+/* Slab domain decomposition of one scene over the GPUs of a node (nothing comparable in the reference,
+ * which runs one OpenMP process).  Every rank builds the SAME scene (same dfr_set_fluid / dfr_add_body calls), then
+ * calls dfr_slab_configure before dfr_finalize: the z cell layers are cut into n_ranks ranges of equal particle count,
+ * the context keeps its range plus one support radius of ghost particles, and dfr_step exchanges boundary layers,
+ * residuals, the CFL maximum and the per-body force/torque/Jacobian rows with NCCL (NVLink) on the context's stream.
+ * id_bytes comes from dfr_slab_unique_id on rank 0 and is distributed by the caller (torch.distributed, MPI, a file).
+ * Results equal the single-context run up to summation order.  Parity dumps (dfr_download_fluid) write only the ids a
+ * rank owns; rigid bodies are replicated.  Not available with emitters or the rigid contact solver. */
+#define DFR_SLAB_ID_BYTES 128
+int dfr_slab_unique_id(char out[DFR_SLAB_ID_BYTES]);
+int dfr_slab_configure(dfr_context *ctx, int rank, int n_ranks, const char id_bytes[DFR_SLAB_ID_BYTES]);
+/* out = { fluid particles owned, ghost particles held, bytes exchanged over NVLink since reset, number of slabs } */
+int dfr_slab_info(dfr_context *ctx, int64_t out[4]);
+
 /* Ends scene construction: uploads everything, computes the Akinci boundary volumes
  * (Simulation::updateBoundaryVolume, Simulation.cpp:831-902) and snapshots the initial state in
  * HBM so that dfr_reset() is a device-to-device copy (replaces SimulatorBase::reset's re-parse,
