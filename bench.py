@@ -7,8 +7,12 @@ Contract (see DESIGN.md "Measurement"):
                                                               (oracle/_ref when built, else the oracle port)
 A "step" is one SimulatorBase::timeStepNoGUI body (TimeStepDiffDFSPH::step + sensitivity chain rule + rigid
 update) over the synthetic dam break with 4 dynamic rigid boxes and 2^20 fluid particles (BASELINE.json
-configs[4], the configuration the north-star's throughput target is quoted on).  For N > 1 every rank runs an
-independent rollout of that scene (population sharding, no data-path collective): weak scaling.
+configs[4], the configuration the north-star's throughput target is quoted on).  For N > 1 (weak scaling, 2^20 particles
+per GPU) there are two shardings, `--mode`:
+  slab      (default) ONE scene of N x 2^20 particles, slab-decomposed over the N GPUs: boundary-layer particles, ghost
+            updates of every gathered array, residuals, the CFL maximum and the rigid force/torque/Jacobian rows travel
+            over NVLink (NCCL) inside every step (BASELINE.json configs[4])
+  rollouts  N independent rollouts of the 2^20-particle scene (population sharding, configs[3]); no data-path collective
 """
 from __future__ import annotations
 
@@ -188,7 +192,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, args.mode),
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -196,11 +200,16 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, mode="slab"):
+    l2 = "working set per step (~0.5 GB of particle state and neighbour lists per GPU) exceeds the 126 MB L2; no flush needed"
+    if n_gpus > 1 and mode == "slab":
+        return {"workload": f"synthetic dam break + {N_BOXES} dynamic rigid boxes, ONE scene of {n_gpus} x {N_PARTICLES} fluid particles "
+                            f"(BASELINE.json configs[4]); forward step + force/torque Jacobians + sensitivity chain rule",
+                "particles_per_gpu": N_PARTICLES, "rollouts": 1,
+                "parallelism": f"slab domain decomposition x{n_gpus} (NCCL/NVLink halo exchange per kernel pass)", "l2": l2}
     return {"workload": f"synthetic dam break + {N_BOXES} dynamic rigid boxes, {N_PARTICLES} fluid particles per rollout "
                         f"(BASELINE.json configs[4]); forward step + force/torque Jacobians + sensitivity chain rule",
-            "particles_per_gpu": N_PARTICLES, "rollouts": n_gpus, "parallelism": f"independent rollouts x{n_gpus}",
-            "l2": "working set per step (~0.5 GB of particle state and neighbour lists) exceeds the 126 MB L2; no flush needed"}
+            "particles_per_gpu": N_PARTICLES, "rollouts": n_gpus, "parallelism": f"independent rollouts x{n_gpus}", "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,6 +219,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("DFR_BENCH_MODE", "slab"), choices=["slab", "rollouts"],
+                    help="sharding for --gpus > 1: one slab-decomposed scene (default) or independent rollouts")
     ap.add_argument("--particles", type=int, default=N_PARTICLES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -238,9 +249,21 @@ def main():
     from difffr_b200 import scenes
     from difffr_b200.cabi import Context
 
-    n_particles = args.particles
+    slab = world > 1 and args.mode == "slab"
+    n_particles = args.particles * (world if slab else 1)
     scene = make_scene(n_particles)
-    ctx = scenes.build_context(lambda **k: Context(device=local_rank, **k), scene, **CFG)
+
+    def make_ctx(**k):
+        ctx = Context(device=local_rank, **k)
+        if slab:  # every rank builds the same scene and keeps one slab of it
+            ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                ident = torch.frombuffer(bytearray(ctx.slab_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(ident, 0)
+            ctx.slab_configure(rank, world, ident.cpu().numpy().tobytes())
+        return ctx
+
+    ctx = scenes.build_context(make_ctx, scene, **CFG)
     nf = ctx.num_fluid
     dyn = [i for i, b in enumerate(scene["bodies"]) if b["dynamic"]]
 
@@ -296,6 +319,9 @@ def main():
     h2d_per_step = (64 * nf) / e2e_steps + 48 * len(dyn)
     d2h_per_step = len(dyn) * (13 + 4 * 9 + 2 * 12 + 2 * 9) * 8 + 8 * 40
     e2e_psteps = nf * e2e_steps
+    slab_info = ctx.slab_info() if slab else None
+    if slab:  # nf is the whole scene; every rank uploads / steps its share
+        e2e_psteps = (i1.total_particle_steps - i0.total_particle_steps) / args.steps * e2e_steps
 
     # ---- per-kernel launch durations, live, CUDA events on the context's stream ----
     ctx.set_profiling(True)
@@ -303,6 +329,7 @@ def main():
     prof = ctx.kernel_profile()
     ctx.set_profiling(False)
     info_p = ctx.step_info()
+    nf_rank = info_p.num_fluid_particles  # fluid particles this rank computes (all of them unless slab-decomposed)
 
     # ---- aggregate over ranks: max time, sum of work ----
     if dist is not None:
@@ -338,7 +365,7 @@ def main():
     nf_mean = nbar  # fluid + boundary neighbours per particle
     bytes_fn = KERNEL_BYTES.get(top_name)
     if bytes_fn is not None:
-        top_bytes = bytes_fn(nf_mean, 0.0) * nf
+        top_bytes = bytes_fn(nf_mean, 0.0) * nf_rank
         achieved = top_bytes / (top_ms / top_n * 1e-3) / 1e9
     else:
         top_bytes, achieved = None, None
@@ -360,7 +387,7 @@ def main():
             pass
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
         ref_so = os.path.join(ROOT, "oracle", "_ref", "fast", "libref.so")
         if os.path.exists(ref_so):
@@ -378,7 +405,7 @@ def main():
         "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, args.mode),
         "wall_ms_per_step": wall_ms / args.steps,
         "solver": {"mean_neighbors": nbar, "divergence_iters": D, "pressure_iters": P, "h": i1.time_step_size},
         "clocks": clocks,
@@ -387,6 +414,8 @@ def main():
                 "what": "dfr_load_fluid_state from pinned host arrays + per step: dfr_set_init_v_omega, dfr_step(1), "
                         "dfr_get_body_state + 8x dfr_get_body_grad per dynamic body"},
         "gpu_launches": int(launches_all),
+        "slab": ({"owned_rank0": slab_info["owned"], "ghosts_rank0": slab_info["ghosts"],
+                  "nvlink_bytes_per_step_rank0": slab_info["exchanged_bytes"] / max(e2e_steps, 1)} if slab else None),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
