@@ -95,7 +95,7 @@ SYMBOLS = [
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
     "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
-    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_unique_id", "slab_configure", "slab_info",
+    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_plan", "slab_unique_id", "slab_configure", "slab_info",
 ]
 
 GRAD_NAMES = [
@@ -129,6 +129,22 @@ def default_library():
     if _default_lib is None:
         _default_lib = load_library()
     return _default_lib
+
+
+def slab_plan(z, z_origin, cell, nz, reach, n_ranks, lib=None):
+    """Cell-aligned cut of the z layers into `n_ranks` slabs of (nearly) equal particle count: `dfr_slab_plan`, the
+    host-side planner `dfr_finalize` uses on a slab-decomposed context.  Returns the n_ranks + 1 plane indices."""
+    lib = lib if lib is not None else default_library()
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    planes = np.zeros(n_ranks + 1, dtype=np.int32)
+    f = lib.dfr_slab_plan
+    f.restype = C.c_int
+    f.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int32)]
+    rc = f(float(z_origin), 1.0 / float(cell), int(nz), int(reach), z.size, z.ctypes.data_as(C.POINTER(C.c_double)), int(n_ranks),
+           planes.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise DfrError(rc, "slab plan: a slab would be thinner than two support radii")
+    return planes
 
 
 def _dptr(a):

@@ -98,6 +98,8 @@ struct dfr_context {
   std::vector<int> h_borig;  // after the static sort
 
   DevBuf<BodyDev> dBodies;
+  BodyDev *h_bodies = nullptr;  // pinned mirror of dBodies, refreshed with the state read-back that ends every dfr_step
+  bool bodies_mirrored = false;
   DevBuf<MgrBlock> dMgr;
   DevBuf<double> acc_rows;
   DevBuf<int> blk_body, blk_first;
@@ -867,6 +869,7 @@ int launch_step(dfr_context *c) {
 }
 
 int reset_device_state(dfr_context *c) {
+  c->bodies_mirrored = false;
   if (c->cfg.use_rigid_contact_solver) {
     if (!c->contact_ready) {
       int rc = contact_init(c);
@@ -1047,6 +1050,7 @@ void dfr_destroy(dfr_context *c) {
   }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->hSt) cudaFreeHost(c->hSt);
+  if (c->h_bodies) cudaFreeHost(c->h_bodies);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1088,9 +1092,10 @@ int dfr_add_body(dfr_context *c, int64_t n, const double *x_local, int is_dynami
 int dfr_set_init_v_omega(dfr_context *c, int body, const double v0[3], const double omega0[3]) {
   if (!c || body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
   HostBody &hb = c->bodies[body];
+  const bool same = (!v0 || std::memcmp(hb.init_v, v0, sizeof(hb.init_v)) == 0) && (!omega0 || std::memcmp(hb.init_w, omega0, sizeof(hb.init_w)) == 0);
   if (v0) std::memcpy(hb.init_v, v0, sizeof(hb.init_v));
   if (omega0) std::memcpy(hb.init_w, omega0, sizeof(hb.init_w));
-  if (c->finalized) {  // SimulationDataDiffDFSPH::get_init_v_rb is read at every beginStep
+  if (c->finalized && !same) {  // SimulationDataDiffDFSPH::get_init_v_rb is read at every beginStep
     cudaSetDevice(c->device);
     hb.dev0.init_v = mk3(hb.init_v[0], hb.init_v[1], hb.init_v[2]);
     hb.dev0.init_omega = mk3(hb.init_w[0], hb.init_w[1], hb.init_w[2]);
@@ -1119,6 +1124,29 @@ int dfr_add_emitter(dfr_context *c, int width, int height, const double position
   e.next_emit_time = emit_start;
   e.emit_counter = 0;
   c->h_emitters.push_back(e);
+  return DFR_OK;
+}
+
+// Host-only: cut nz cell layers into n_ranks ranges holding (nearly) equal numbers of particles.
+int dfr_slab_plan(double z_origin, double inv_cell, int nz, int reach, int64_t n, const double *z, int n_ranks, int32_t *planes) {
+  if (nz <= 0 || n_ranks < 1 || !planes || (n > 0 && !z)) return DFR_ERR_INVALID;
+  std::vector<int64_t> hist(nz, 0);
+  for (int64_t i = 0; i < n; i++) {
+    int zc = (int)std::floor((z[i] - z_origin) * inv_cell);  // the arithmetic of cell_of (dfr_kernels.cuh), global origin
+    zc = std::min(std::max(zc, 0), nz - 1);
+    hist[zc]++;
+  }
+  planes[0] = 0;
+  planes[n_ranks] = nz;
+  int64_t cum = 0;
+  int k = 1;
+  for (int zc = 0; zc < nz && k < n_ranks; zc++) {
+    cum += hist[zc];
+    while (k < n_ranks && cum >= (n * (int64_t)k) / n_ranks) planes[k++] = zc + 1;
+  }
+  for (; k < n_ranks; k++) planes[k] = nz;
+  for (int r = 0; r < n_ranks; r++)
+    if (n_ranks > 1 && planes[r + 1] - planes[r] < 2 * reach + 1) return DFR_ERR_INVALID;
   return DFR_OK;
 }
 
@@ -1293,16 +1321,13 @@ int dfr_finalize(dfr_context *c) {
       hist[z]++;
     }
     std::vector<int> planes(S.n + 1, 0);
-    planes[S.n] = G.nz;
-    int64_t cum = 0;
-    int k = 1;
-    for (int z = 0; z < G.nz && k < S.n; z++) {
-      cum += hist[z];
-      while (k < S.n && cum >= (c->nf0 * (int64_t)k) / S.n) planes[k++] = z + 1;
-    }
-    for (int r = 0; r < S.n; r++)
-      if (planes[r + 1] - planes[r] < 2 * G.reach + 1)
+    {
+      std::vector<double> zs(c->nf0);
+      for (int64_t i = 0; i < c->nf0; i++) zs[i] = c->h_fx[3 * i + 2];
+      const int prc = dfr_slab_plan(G.oz, G.inv_cell, G.nz, G.reach, c->nf0, zs.data(), S.n, planes.data());
+      if (prc == DFR_ERR_INVALID)
         return fail(c, DFR_ERR_INVALID, "slab decomposition: a slab would be thinner than two support radii (too many ranks for this scene)");
+    }
     const int zlo = planes[S.rank], zhi = planes[S.rank + 1];
     const int pad = 2 * G.reach + 2;
     S.G.reach = G.reach;
@@ -1372,6 +1397,7 @@ int dfr_finalize(dfr_context *c) {
   CU(c->bvol.alloc(NB));
   CU(c->dBodies.alloc(std::max<size_t>(c->bodies.size(), 1)));
   CU(c->dMgr.alloc(std::max<size_t>(c->bodies.size() * c->bodies.size(), 1)));
+  if (cudaMallocHost((void **)&c->h_bodies, std::max<size_t>(c->bodies.size(), 1) * sizeof(BodyDev)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
   const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
@@ -1497,6 +1523,7 @@ int dfr_reset(dfr_context *c) {
 int dfr_reset_gradient(dfr_context *c) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
+  c->bodies_mirrored = false;
   if (c->P.n_bodies > 0) {
     LAUNCH(c, k_reset_gradient, 1, 32, c->P, c->dBodies.p);
     if (c->acc_rows.n) CU(cudaMemsetAsync(c->acc_rows.p, 0, c->acc_rows.n * sizeof(double), c->stream));
@@ -1516,14 +1543,18 @@ int dfr_set_gradient_mode(dfr_context *c, int mode) {
 int dfr_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
+  c->bodies_mirrored = false;
   CU(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; s++) {
     int rc = launch_step(c);
     if (rc) return rc;
   }
   CU(cudaEventRecord(c->ev1, c->stream));
+  if (!c->bodies.empty())
+    CU(cudaMemcpyAsync(c->h_bodies, c->dBodies.p, c->bodies.size() * sizeof(BodyDev), cudaMemcpyDeviceToHost, c->stream));
   int rc = sync_state(c);
   if (rc) return rc;
+  c->bodies_mirrored = !c->bodies.empty();
   if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
   CU(cudaGetLastError());
   float ms = 0.f;
@@ -1535,6 +1566,7 @@ int dfr_step(dfr_context *c, int n_steps) {
 int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
+  c->bodies_mirrored = false;
   CU(cudaEventRecord(c->ev0, c->stream));
   int s = 0;
   while (s < max_steps) {
@@ -1576,12 +1608,18 @@ int dfr_get_step_info(dfr_context *c, dfr_step_info *info) {
   return DFR_OK;
 }
 
+// The getters below read the host mirror: one D2H of all body records per step (riding on the step's own state
+// read-back) instead of one blocking copy per getter call - the scripts read 9 blocks per body and step.
 static int fetch_body(dfr_context *c, int body, BodyDev &B) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   if (body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
-  cudaSetDevice(c->device);
-  CU(cudaMemcpyAsync(&B, c->dBodies.p + body, sizeof(BodyDev), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (!c->bodies_mirrored) {
+    cudaSetDevice(c->device);
+    CU(cudaMemcpyAsync(c->h_bodies, c->dBodies.p, c->bodies.size() * sizeof(BodyDev), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bodies_mirrored = true;
+  }
+  B = c->h_bodies[body];
   return DFR_OK;
 }
 
@@ -1600,6 +1638,7 @@ int dfr_set_body_velocity(dfr_context *c, int body, const double v[3], const dou
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   if (body < 0 || body >= (int)c->bodies.size()) return fail(c, DFR_ERR_INVALID, "bad body index");
   cudaSetDevice(c->device);
+  c->bodies_mirrored = false;
   BodyDev *d = c->dBodies.p + body;
   if (v) {
     const d3 t = mk3(v[0], v[1], v[2]);

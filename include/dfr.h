@@ -122,6 +122,10 @@ int dfr_set_init_v_omega(dfr_context *ctx, int body, const double v0[3], const d
  * Results equal the single-context run up to summation order.  Parity dumps (dfr_download_fluid) write only the ids a
  * rank owns; rigid bodies are replicated.  Not available with emitters or the rigid contact solver. */
 #define DFR_SLAB_ID_BYTES 128
+/* The cut dfr_finalize uses, callable on its own (host only, no device needed): z is the z coordinate of every fluid
+ * particle, cell layer = floor((z - z_origin) * inv_cell) clamped to [0, nz).  planes gets n_ranks + 1 layer indices,
+ * rank r owns layers [planes[r], planes[r+1]).  DFR_ERR_INVALID if a slab would be thinner than 2 * reach + 1 layers. */
+int dfr_slab_plan(double z_origin, double inv_cell, int nz, int reach, int64_t n, const double *z, int n_ranks, int32_t *planes);
 int dfr_slab_unique_id(char out[DFR_SLAB_ID_BYTES]);
 int dfr_slab_configure(dfr_context *ctx, int rank, int n_ranks, const char id_bytes[DFR_SLAB_ID_BYTES]);
 /* out = { fluid particles owned, ghost particles held, bytes exchanged over NVLink since reset, number of slabs } */
