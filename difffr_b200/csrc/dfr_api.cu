@@ -889,11 +889,11 @@ int reset_device_state(dfr_context *c) {
     CU(cudaMemcpyAsync(c->vel[0].p, c->vel_init.p, n * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->kappa[0].p, c->kappa_init.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->kappav[0].p, c->kappav_init.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    std::vector<int> ids(c->nf_cap);
-    for (int64_t i = 0; i < c->nf_cap; i++) ids[i] = (int)i;
-    if (c->slab.on) std::copy(c->h_ids0.begin(), c->h_ids0.end(), ids.begin());
-    CU(cudaMemcpyAsync(c->pid[0].p, ids.data(), c->nf_cap * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    LAUNCH(c, k_iota_i32, cdiv(c->nf_cap, 256), 256, c->pid[0].p, (size_t)c->nf_cap);  // particle ids = input order
+    if (c->slab.on) {  // a slab holds a subset: its ids at t = 0
+      CU(cudaMemcpyAsync(c->pid[0].p, c->h_ids0.data(), c->h_ids0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
     CU(cudaMemsetAsync(c->pstate[0].p, 0, c->nf_cap * sizeof(int), c->stream));
     CU(cudaMemsetAsync(c->sgp.p, 0, c->nf_cap * sizeof(double4), c->stream));
     CU(cudaMemsetAsync(c->acc.p, 0, c->nf_cap * sizeof(double4), c->stream));
@@ -1491,6 +1491,23 @@ int dfr_load_fluid_state(dfr_context *c, const double *x, const double *v, const
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
   const int64_t n = c->nf_loc0;  // arrays are indexed by particle id; a slab keeps the ids it owned at t = 0
+  if (!c->slab.on) {
+    // straight from the caller's (ideally pinned) arrays: H2D into scratch, repack on the device
+    double *stage = (double *)c->acc.p;  // n double4 of scratch >= 3 n doubles; reset clears it afterwards
+    if (x && n) {
+      CU(cudaMemcpyAsync(stage, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(c, k_xyz_to_rec, cdiv(n, 256), 256, stage, c->pos_init.p, (int)n);
+    }
+    if (v && n) {
+      double *stage_v = (double *)c->sgp.p;
+      CU(cudaMemcpyAsync(stage_v, v, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(c, k_xyz_to_rec, cdiv(n, 256), 256, stage_v, c->vel_init.p, (int)n);
+    }
+    if (kappa && n) CU(cudaMemcpyAsync(c->kappa_init.p, kappa, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (kappa_v && n) CU(cudaMemcpyAsync(c->kappav_init.p, kappa_v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return reset_device_state(c);
+  }
   auto id_of = [&](int64_t k) { return c->slab.on ? (int64_t)c->h_ids0[k] : k; };
   std::vector<double4> tmp(n);
   std::vector<double> tmp1(n);
@@ -1740,8 +1757,8 @@ int dfr_download_fluid(dfr_context *c, int field, double *out) {
   int rc = sync_state(c);
   if (rc) return rc;
   // slab mode: only the particles this rank owns are written (entries of other ids stay untouched; the caller merges)
-  const int i0 = c->hSt->own_begin;
-  const int n = c->hSt->own_end - i0;
+  const int i0 = c->slab.on ? c->hSt->own_begin : 0;
+  const int n = c->slab.on ? c->hSt->own_end - i0 : c->hSt->nf;
   if (n <= 0) return DFR_OK;
   std::vector<int> ids(n);
   CU(cudaMemcpy(ids.data(), c->pid[c->cur].p + i0, n * sizeof(int), cudaMemcpyDeviceToHost));

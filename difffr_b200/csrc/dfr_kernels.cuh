@@ -253,6 +253,11 @@ __global__ void k_fill_i32(int *p, int v, size_t n) {
   if (i < n) p[i] = v;
 }
 
+__global__ void k_iota_i32(int *p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+
 // exclusive scan of unsigned ints, 3 kernels (block scan, scan of block sums, add offsets)
 #define SCAN_THREADS 512
 #define SCAN_ITEMS 8
@@ -423,6 +428,11 @@ __global__ void k_permute_fluid(const StepState *st, const int *sorted_src, cons
   kappav_out[i] = kappav_in[s];
   id_out[i] = id_in[s];
   state_out[i] = state_in[s];
+}
+// xyz AoS (what crosses the C ABI) -> double4 records
+__global__ void k_xyz_to_rec(const double *xyz, double4 *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_double4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 0.0);
 }
 // one-time physical sort of the static boundary particles
 __global__ void k_permute_boundary(int n, const int *sorted_src, const double4 *pos_in, const double4 *x0_in, const int *body_in,

@@ -310,7 +310,7 @@ __global__ void k_body_update(const __grid_constant__ Params P, StepState *st, B
   if (b == 0 && phase != BODY_POST) {
     st->last_iters = st->prs_iters;
     st->total_iters += st->prs_iters;
-    st->total_particle_steps += st->own_end - st->own_begin;
+    st->total_particle_steps += P.slab ? st->own_end - st->own_begin : st->nf;
     st->time += st->h_step;
     st->finished = (st->time >= P.target_time + P.uniform_acc_time) ? 1 : 0;
   }
