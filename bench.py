@@ -377,7 +377,7 @@ def main():
         "kernel_avg_ms": top_ms / top_n, "algorithmic_bytes_per_launch": top_bytes,
         "whole_step": {"bytes_per_particle_step": step_bytes, "achieved": value * step_bytes / 1e9,
                        "frac": value * step_bytes / 1e9 / peak, "mean_neighbors": nbar, "D": D, "P": P},
-        "kernels_ms_per_step": {k: v[0] / max(3, min(10, args.steps)) for k, v in sorted(classes.items(), key=lambda kv: -kv[1][0])[:8]},
+        "kernels_ms_per_step": {k: v[0] / max(3, min(10, args.steps)) for k, v in sorted(classes.items(), key=lambda kv: -kv[1][0])[:16]},
     }
     ncu = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(ncu):
@@ -414,7 +414,7 @@ def main():
                 "what": "dfr_load_fluid_state from pinned host arrays + per step: dfr_set_init_v_omega, dfr_step(1), "
                         "dfr_get_body_state + 8x dfr_get_body_grad per dynamic body"},
         "gpu_launches": int(launches_all),
-        "slab": ({"owned_rank0": slab_info["owned"], "ghosts_rank0": slab_info["ghosts"],
+        "slab": ({"owned_rank0": slab_info["owned"], "ghosts_rank0": slab_info["ghosts"], "ghost_transport": slab_info["transport"],
                   "nvlink_bytes_per_step_rank0": slab_info["exchanged_bytes"] / max(e2e_steps, 1)} if slab else None),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -295,7 +295,8 @@ class Context:
     def slab_info(self):
         out = (C.c_int64 * 4)()
         self._check(self._fn("slab_info")(self._ctx, out))
-        return {"owned": out[0], "ghosts": out[1], "exchanged_bytes": out[2], "slabs": out[3]}
+        return {"owned": out[0], "ghosts": out[1], "exchanged_bytes": out[2], "slabs": abs(out[3]),
+                "transport": "peer stores (cudaIpc over NVLink)" if out[3] < 0 else "nccl send/recv"}
 
     def finalize(self):
         self._check(self._fn("finalize")(self._ctx))

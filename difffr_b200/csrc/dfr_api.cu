@@ -100,6 +100,7 @@ struct dfr_context {
   DevBuf<BodyDev> dBodies;
   BodyDev *h_bodies = nullptr;  // pinned mirror of dBodies, refreshed with the state read-back that ends every dfr_step
   bool bodies_mirrored = false;
+  bool slab_needs_p2p_setup = false;
   DevBuf<MgrBlock> dMgr;
   DevBuf<double> acc_rows;
   DevBuf<int> blk_body, blk_first;
@@ -138,6 +139,16 @@ struct dfr_context {
     int *h_counts = nullptr;             // pinned, 4 ints
     DevBuf<double> body_buf;
     long long exchanged_bytes = 0;       // NVLink traffic of the steps since reset (both directions, this rank)
+    // peer-memory transport of the ghost updates (cudaIpc-mapped neighbour buffers, NVLink stores from the producing
+    // kernels + one flag per pass); falls back to NCCL send/recv when the mapping is not available
+    bool p2p = false;
+    double4 *peer_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *peer_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *peer_lo_flags = nullptr, *peer_hi_flags = nullptr;
+    void *ipc_opened[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf<unsigned long long> flags;    // [0] raised by the low neighbour, [1] by the high one
+    DevBuf<char> ipc_stage;
+    unsigned long long pass = 0;
+    int lo_nb_own_end = 0;               // where my low boundary layer starts in the low neighbour's arrays
   } slab;
 
   // SM-local scheduling of the gather kernels (dfr_kernels.cuh: VSched)
@@ -427,6 +438,7 @@ int compute_boundary_volumes(dfr_context *c) {
 int sync_state(dfr_context *c) {
   CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->hSt->error_flags & 32) return fail(c, DFR_ERR_STATE, "slab: timed out waiting for a neighbour's ghost rows (did a peer fail?)");
   if (c->hSt->error_flags & 16) return fail(c, DFR_ERR_STATE, "slab: a particle moved further than one ghost layer in one step");
   if (c->hSt->error_flags & 8) return fail(c, DFR_ERR_CAPACITY, "slab: export buffer too small");
   if (c->hSt->error_flags) {
@@ -492,9 +504,39 @@ NcclApi *nccl_api(std::string *why) {
     if (r__ != ncclSuccess) return fail(c, DFR_ERR_CUDA, std::string(#call) + ": " + nccl_api(nullptr)->GetErrorString(r__)); \
   } while (0)
 
+enum { GA_XK = 0, GA_XRHO = 1, GA_NORMAL = 2, GA_VEL0 = 3, GA_VEL1 = 4 };
+// where the producing kernel has to mirror its boundary-layer rows (nothing unless the peer-memory transport is on)
+GhostOut ghost_out(dfr_context *c, int which) {
+  GhostOut g;
+  std::memset(&g, 0, sizeof(g));
+  auto &S = c->slab;
+  if (!S.on || !S.p2p) return g;
+  if (S.G.has_lo) {
+    g.lo = S.peer_lo[which] + S.lo_nb_own_end;  // the low neighbour's ghost_hi range starts at its own_end
+    g.lo_begin = S.h_ranges[0];
+    g.lo_end = S.h_ranges[2];
+  }
+  if (S.G.has_hi) {
+    g.hi = S.peer_hi[which];  // the high neighbour's ghost_lo range starts at 0
+    g.hi_begin = S.h_ranges[3];
+    g.hi_end = S.h_ranges[1];
+  }
+  return g;
+}
+
 // ghost update of one per-particle array (element size `esz` bytes): my boundary layers -> the neighbours' ghost layers
 int slab_sync(dfr_context *c, void *buf, size_t esz) {
   auto &S = c->slab;
+  if (S.p2p) {  // the rows were written by the producing kernel; tell the neighbours and wait for theirs
+    S.pass++;
+    LAUNCH(c, k_slab_signal_wait, 1, 32, S.G.has_lo ? S.peer_lo_flags + 1 : (unsigned long long *)nullptr,
+           S.G.has_hi ? S.peer_hi_flags + 0 : (unsigned long long *)nullptr, (volatile unsigned long long *)S.flags.p, S.pass,
+           5000000000ull, &c->dSt.p->error_flags);
+    const long long rows = (S.G.has_lo ? (S.h_ranges[2] - S.h_ranges[0]) + S.h_ranges[0] : 0) +
+                           (S.G.has_hi ? (S.h_ranges[1] - S.h_ranges[3]) + (S.h_ranges[4] - S.h_ranges[1]) : 0);
+    S.exchanged_bytes += rows * (long long)esz;
+    return DFR_OK;
+  }
   NcclApi *N = nccl_api(nullptr);
   const int own_begin = S.h_ranges[0], own_end = S.h_ranges[1], bl_lo_end = S.h_ranges[2], bl_hi_begin = S.h_ranges[3], nf = S.h_ranges[4];
   char *b = (char *)buf;
@@ -527,6 +569,66 @@ int slab_allreduce(dfr_context *c, void *buf, size_t count, ncclDataType_t type,
     }                                             \
   } while (0)
 
+// Map the neighbours' gathered arrays and flag words into this process (cudaIpc) so that the producing kernels can
+// store boundary rows straight into the neighbours' ghost ranges over NVLink.  All ranks agree (all-reduce) on whether
+// the mapping worked; otherwise everybody stays on NCCL send/recv.  DFR_SLAB_TRANSPORT=nccl forces the fallback.
+int slab_p2p_setup(dfr_context *c) {
+  auto &S = c->slab;
+  NcclApi *N = nccl_api(nullptr);
+  const char *env = getenv("DFR_SLAB_TRANSPORT");
+  int want = !(env && std::string(env) == "nccl");
+  CU(S.flags.alloc(8));
+  const int NH = 6;
+  CU(S.ipc_stage.alloc(3 * NH * sizeof(cudaIpcMemHandle_t) + 16));
+  void *mine[NH] = {c->xk.p, c->xrho.p, c->normal.p, c->vel[0].p, c->vel[1].p, S.flags.p};
+  std::vector<cudaIpcMemHandle_t> h(3 * NH);
+  std::memset(h.data(), 0, h.size() * sizeof(cudaIpcMemHandle_t));
+  int ok = want;
+  for (int k = 0; k < NH && ok; k++)
+    if (cudaIpcGetMemHandle(&h[k], mine[k]) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  const size_t hb = NH * sizeof(cudaIpcMemHandle_t);
+  CU(cudaMemcpyAsync(S.ipc_stage.p, h.data(), hb, cudaMemcpyHostToDevice, c->stream));
+  NC(N->GroupStart());
+  if (S.G.has_lo) {
+    NC(N->Send(S.ipc_stage.p, hb, ncclChar, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(S.ipc_stage.p + hb, hb, ncclChar, S.rank - 1, S.comm, c->stream));
+  }
+  if (S.G.has_hi) {
+    NC(N->Send(S.ipc_stage.p, hb, ncclChar, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(S.ipc_stage.p + 2 * hb, hb, ncclChar, S.rank + 1, S.comm, c->stream));
+  }
+  NC(N->GroupEnd());
+  CU(cudaMemcpyAsync(h.data(), S.ipc_stage.p, 3 * hb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int side = 0; side < 2 && ok; side++) {
+    if (!(side == 0 ? S.G.has_lo : S.G.has_hi)) continue;
+    for (int k = 0; k < NH && ok; k++) {
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h[(1 + side) * NH + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      S.ipc_opened[side * NH + k] = ptr;
+      if (k < 5)
+        (side == 0 ? S.peer_lo : S.peer_hi)[k] = (double4 *)ptr;
+      else
+        (side == 0 ? S.peer_lo_flags : S.peer_hi_flags) = (unsigned long long *)ptr;
+    }
+  }
+  // everybody or nobody
+  int *flag = (int *)(S.ipc_stage.p + 3 * hb);
+  CU(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NC(N->AllReduce(flag, flag, 1, ncclInt, ncclMin, S.comm, c->stream));
+  CU(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  S.p2p = ok != 0;
+  return DFR_OK;
+}
+
 // Step start in slab mode: export the particles that now sit in my boundary layers (or beyond: emigrants), import the
 // neighbours', and re-sort.  Replaces the head of build_neighbors.
 int slab_exchange_and_sort(dfr_context *c) {
@@ -535,7 +637,7 @@ int slab_exchange_and_sort(dfr_context *c) {
   const int a = c->cur, b = 1 - c->cur;
   const int own_begin = S.h_ranges[0], own_end = S.h_ranges[1];
   const int n_own = own_end - own_begin;
-  CU(cudaMemsetAsync(S.counts.p, 0, 4 * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(S.counts.p, 0, 8 * sizeof(int), c->stream));
   LAUNCH(c, k_slab_select, cdiv(n_own, 128), 128, c->P, S.G, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p,
          c->pid[a].p, c->pstate[a].p, S.send_cap, S.s_pos[0].p, S.s_vel[0].p, S.s_misc[0].p, S.s_pos[1].p, S.s_vel[1].p, S.s_misc[1].p,
          S.counts.p, &c->dSt.p->error_flags);
@@ -605,24 +707,25 @@ int slab_exchange_and_sort(dfr_context *c) {
   NC(N->GroupStart());
   if (S.G.has_lo) {
     NC(N->Send(&c->dSt.p->slab_ranges[5], 1, ncclInt, S.rank - 1, S.comm, c->stream));
-    NC(N->Recv(S.counts.p + 2, 1, ncclInt, S.rank - 1, S.comm, c->stream));
+    NC(N->Recv(S.counts.p + 2, 2, ncclInt, S.rank - 1, S.comm, c->stream));  // its bl_hi count, its own_end
   }
   if (S.G.has_hi) {
-    NC(N->Send(&c->dSt.p->slab_ranges[6], 1, ncclInt, S.rank + 1, S.comm, c->stream));
-    NC(N->Recv(S.counts.p + 3, 1, ncclInt, S.rank + 1, S.comm, c->stream));
+    NC(N->Send(&c->dSt.p->slab_ranges[6], 2, ncclInt, S.rank + 1, S.comm, c->stream));  // my bl_hi count, my own_end (ranges[7])
+    NC(N->Recv(S.counts.p + 4, 1, ncclInt, S.rank + 1, S.comm, c->stream));
   }
   NC(N->GroupEnd());
-  CU(cudaMemcpyAsync(S.h_counts, S.counts.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(S.h_counts, S.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   rc = sync_state(c);
   if (rc) return rc;
   std::memcpy(S.h_ranges, c->hSt->slab_ranges, sizeof(S.h_ranges));
   const int ghost_lo = S.h_ranges[0], ghost_hi = S.h_ranges[4] - S.h_ranges[1];
-  if ((S.G.has_lo && S.h_counts[2] != ghost_lo) || (S.G.has_hi && S.h_counts[3] != ghost_hi)) {
+  if ((S.G.has_lo && S.h_counts[2] != ghost_lo) || (S.G.has_hi && S.h_counts[4] != ghost_hi)) {
     char buf[200];
     std::snprintf(buf, sizeof(buf), "slab %d: ghost layers (%d, %d) do not match the neighbours' boundary layers (%d, %d)", S.rank, ghost_lo,
-                  ghost_hi, S.G.has_lo ? S.h_counts[2] : 0, S.G.has_hi ? S.h_counts[3] : 0);
+                  ghost_hi, S.G.has_lo ? S.h_counts[2] : 0, S.G.has_hi ? S.h_counts[4] : 0);
     return fail(c, DFR_ERR_STATE, buf);
   }
+  S.lo_nb_own_end = S.G.has_lo ? S.h_counts[3] : 0;
   return DFR_OK;
 }
 
@@ -660,8 +763,9 @@ int launch_solver(dfr_context *c) {
   double *kap = PRESSURE ? c->kappa[a].p : c->kappav[a].p;
 #define RHO_ARGS                                                                                                             \
   c->P, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
-      c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p
-#define PUSH_ARGS c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0
+      c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p, ghost_out(c, GA_XK)
+#define PUSH_ARGS \
+  c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0, ghost_out(c, GA_VEL0 + c->vcur)
   if (warm) {
     PLAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, RHO_ARGS);
     SLAB_SYNC(c, c->xk.p, sizeof(double4));
@@ -687,7 +791,10 @@ int launch_solver(dfr_context *c) {
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
         LAUNCH(c, k_solver_decide<PRESSURE>, 1, 32, c->P, c->dSt.p);
-        SLAB_SYNC(c, c->xk.p, sizeof(double4));
+        // peer-store transport: every rank's k_rho (and with it its stores into my ghost range) precedes its
+        // contribution to the all-reduce in stream order, so the completed all-reduce already orders them before my
+        // next kernel; with NCCL send/recv the rows still have to be shipped
+        if (!c->slab.p2p) SLAB_SYNC(c, c->xk.p, sizeof(double4));
       }
     }
     c->prof_solver = -1;
@@ -797,8 +904,10 @@ int launch_step(dfr_context *c) {
   g = cdiv(n, 128);
   int a = c->cur;
   PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
-         c->sgp.p, c->xrho.p);
-  SLAB_SYNC(c, c->xrho.p, sizeof(double4));
+         c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
+  // x|rho is first gathered by k_normals / k_nonpressure: with peer stores any later flag (the divergence solve has
+  // several) covers it
+  if (!(c->slab.p2p && c->cfg.enable_divergence_solver)) SLAB_SYNC(c, c->xrho.p, sizeof(double4));
   bool scale_kv = false;
   if (c->cfg.enable_divergence_solver) {
     rc = launch_solver<false>(c);
@@ -807,13 +916,14 @@ int launch_step(dfr_context *c) {
   }
   if (c->cfg.surface_tension_method == 2)
   {
-    PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p);
+    PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p, ghost_out(c, GA_NORMAL));
     SLAB_SYNC(c, c->normal.p, sizeof(double4));
   }
   PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
-         c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p);
+         c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p,
+         ghost_out(c, GA_VEL0 + (1 - c->vcur)));
   c->vcur = 1 - c->vcur;
-  SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
+  if (!c->slab.p2p) SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));  // peer stores: ordered by the CFL all-reduce below
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
   if (c->slab.on) {  // max |v + a h|^2 over all slabs (ordered bits of positive doubles)
     rc = slab_allreduce(c, &c->dSt.p->cfl_max_bits, 1, ncclUint64, ncclMax);
@@ -1040,7 +1150,9 @@ void dfr_destroy(dfr_context *c) {
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
   c->sched_ctr.free();
   for (int k = 0; k < 2; k++) { c->slab.s_pos[k].free(); c->slab.s_vel[k].free(); c->slab.s_misc[k].free(); }
-  c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free();
+  for (void *p : c->slab.ipc_opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free(); c->slab.flags.free(); c->slab.ipc_stage.free();
   if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
   if (c->slab.comm && nccl_api(nullptr)) nccl_api(nullptr)->CommDestroy(c->slab.comm);
   c->c_vol0.free(); c->c_dens0.free(); c->c_dens.free(); c->c_records.free(); c->c_vel.free(); c->c_order.free();
@@ -1187,7 +1299,7 @@ int dfr_slab_info(dfr_context *c, int64_t out[4]) {
   out[0] = c->hSt->own_end - c->hSt->own_begin;
   out[1] = c->hSt->nf - out[0];
   out[2] = c->slab.exchanged_bytes;
-  out[3] = c->slab.on ? c->slab.n : 1;
+  out[3] = c->slab.on ? (c->slab.p2p ? -c->slab.n : c->slab.n) : 1;  // negative: ghost updates travel as peer stores
   return DFR_OK;
 }
 
@@ -1372,10 +1484,11 @@ int dfr_finalize(dfr_context *c) {
       CU(S.s_pos[k].alloc(S.send_cap)); CU(S.s_vel[k].alloc(S.send_cap)); CU(S.s_misc[k].alloc(S.send_cap));
     }
     CU(S.r_misc.alloc(2 * (size_t)S.send_cap));
-    CU(S.counts.alloc(4));
+    CU(S.counts.alloc(8));
     CU(S.body_buf.alloc(std::max<size_t>(c->bodies.size(), 1) * ACC_N));
-    if (cudaMallocHost((void **)&S.h_counts, 4 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
+    if (cudaMallocHost((void **)&S.h_counts, 8 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   }
+  c->slab_needs_p2p_setup = c->slab.on;
   CU(c->dEmitters.alloc(std::max<size_t>(c->h_emitters.size(), 1)));
   const int nc = P.grid.ncells;
   CU(c->dSt.alloc(1));
@@ -1414,6 +1527,11 @@ int dfr_finalize(dfr_context *c) {
   const size_t nwarp = (N + 31) / 32;
   CU(c->idx_f.alloc(nwarp * 32 * (size_t)c->cap_f)); CU(c->idx_b.alloc(nwarp * 32 * (size_t)c->cap_b));
   CU(c->idx_d.alloc(c->cap_d)); CU(c->off_d.alloc(ND + 1));
+  if (c->slab_needs_p2p_setup) {  // needs the gathered arrays to exist
+    int prc = slab_p2p_setup(c);
+    if (prc) return prc;
+    c->slab_needs_p2p_setup = false;
+  }
 
   // ---- accumulator blocks of the boundary-side kernel: one body per block ----
   std::vector<int> blk_body, blk_first;

@@ -119,6 +119,21 @@ __device__ __forceinline__ double4 ld4(const double4 *p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Slab decomposition, peer-memory transport (dfr_slab.cuh): the kernel that produces a gathered array also writes the
+// rows of its boundary layers straight into the neighbour GPU's ghost range (stores over NVLink to a cudaIpc-mapped
+// peer buffer), so that a ghost update costs no extra pass over the data and no collective launch - only a flag.
+// lo / hi are null on a single context or with the NCCL transport.
+// ---------------------------------------------------------------------------------------------
+struct GhostOut {
+  double4 *lo, *hi;  // peer arrays, already offset to the first ghost row that mirrors my boundary layer
+  int lo_begin, lo_end, hi_begin, hi_end;  // my boundary-layer rows
+};
+__device__ __forceinline__ void ghost_store(const GhostOut &g, int i, const double4 &v) {
+  if (g.lo && i >= g.lo_begin && i < g.lo_end) stg4(g.lo + (i - g.lo_begin), v);
+  if (g.hi && i >= g.hi_begin && i < g.hi_end) stg4(g.hi + (i - g.hi_begin), v);
+}
+
+// ---------------------------------------------------------------------------------------------
 // cell coordinates
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -579,7 +594,7 @@ __global__ void k_store_volume(double4 *bpos, const double *vol, int n_b) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ Params P, const StepState *st, const double4 *pos, const double4 *bpos,
                                                          NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp, double4 *xrho,
-                                                         const VSched S) {
+                                                         const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
@@ -611,6 +626,7 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
   density[i] = dens * P.density0;
   // (x, rho) record: k_normals gathers position and density of a neighbour in one 256-bit load
   stg4(xrho + i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
+  ghost_store(GO, i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
   const double denom = S + dot(G, G);
   factor[i] = (denom > DFR_EPS) ? -1.0 / denom : 0.0;
   sgp[i] = make_double4(-G.x, -G.y, -G.z, 0.0);
@@ -627,7 +643,8 @@ enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
 template <bool PRESSURE, int MODE>
 __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
-                                              const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const VSched S) {
+                                              const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const GhostOut GO,
+                                              const VSched S) {
   vsched_prologue(S);
   if (MODE == RHO_ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
@@ -677,11 +694,13 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
       if (state[i] != 0) kap = 0.0;  // the reference zeroes these in its second loop (:1008-1012 / :1737-1741)
       kappa[i] = kap;
       stg4(xk + i, make_double4(pi.x, pi.y, pi.z, kap));
+      ghost_store(GO, i, make_double4(pi.x, pi.y, pi.z, kap));
     } else {
       const double b = PRESSURE ? rho - 1.0 : rho;
       const double ks = PRESSURE ? b * factor[i] / (h * h) : b * factor[i] / h;
       // (x, k) record: the push and the boundary-side kernel gather position and stiffness together
       stg4(xk + i, make_double4(pi.x, pi.y, pi.z, ks));
+      ghost_store(GO, i, make_double4(pi.x, pi.y, pi.z, ks));
     }
   }
   if (MODE == RHO_ITER) {
@@ -748,7 +767,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
 template <bool PRESSURE, bool ITER>
 __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
                                                NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa,
-                                               const VSched S) {
+                                               const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   if (ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
@@ -786,6 +805,7 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
   v.y += dv.y;
   v.z += dv.z;
   vel[i] = v;
+  ghost_store(GO, i, v);
   }
 }
 
@@ -997,7 +1017,7 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_co
 // maximum (Simulation.cpp:542-575), fused.  kappa_v *= h_step of divergenceSolve (:870-880) rides along.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params P, const StepState *st, const double4 *xrho, NbrList lf,
-                                                  double4 *normal, const VSched S) {
+                                                  double4 *normal, const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
   const int i = vb_ * 128 + threadIdx.x;
@@ -1013,13 +1033,14 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
       });
   // w carries the particle's density so that the force pass gathers (n_j, rho_j) in one record
   stg4(normal + i, make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, pi.w));
+  ghost_store(GO, i, make_double4(P.support_radius * n.x, P.support_radius * n.y, P.support_radius * n.z, pi.w));
   }
 }
 
 __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
                                                       const double4 *bvel, NbrList lf, NbrList lb,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
-                                                      double4 *acc_out, double4 *vel_out, const VSched S) {
+                                                      double4 *acc_out, double4 *vel_out, const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   const int nf = st->nf;
   const double h = st->h_step;
@@ -1088,10 +1109,9 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
     acc_out[i] = make_double4(a.x, a.y, a.z, 0.0);
     const d3 vn = mk3(vi.x + h * a.x, vi.y + h * a.y, vi.z + h * a.z);
     mag = dot(vn, vn);  // CFL uses (vel + accel*h) with the OLD h for every particle (Simulation.cpp:561-566)
-    if (state[i] == 0)
-      vel_out[i] = make_double4(vn.x, vn.y, vn.z, 0.0);
-    else
-      vel_out[i] = vi;
+    const double4 vo = (state[i] == 0) ? make_double4(vn.x, vn.y, vn.z, 0.0) : vi;
+    vel_out[i] = vo;
+    ghost_store(GO, i, vo);
     if (scale_kappav) kappav[i] *= h;
   }
 #pragma unroll

@@ -114,6 +114,7 @@ __global__ void k_slab_ranges(const __grid_constant__ Params P, const SlabGeom G
   st->slab_ranges[4] = nf;
   st->slab_ranges[5] = st->slab_ranges[2] - own_begin;  // particles in my low / high boundary layer
   st->slab_ranges[6] = own_end - st->slab_ranges[3];
+  st->slab_ranges[7] = own_end;  // sent together with [6]: the high neighbour mirrors its low boundary layer behind my owned range
   // particles that escaped beyond the ghost layers cannot be handled (they would need more than one hop)
   const int ghost_lo_begin = G.has_lo ? (int)cell_start[(size_t)(G.own_zlo - G.reach) * layer] : 0;
   const int ghost_hi_end = G.has_hi ? (int)cell_start[(size_t)(G.own_zhi + G.reach) * layer] : nf;
@@ -139,6 +140,34 @@ __global__ void k_solver_decide(const __grid_constant__ Params P, StepState *st)
     st->div_iters = it;
     const bool chk = (avg <= eta);
     if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
+  }
+}
+
+// Peer-memory transport: "my boundary rows of this pass are in your ghost range" / "are yours in mine?".
+// One thread: release my writes at system scope, raise the counter in both neighbours' flag words, then spin on mine.
+// flags[0] is written by the low neighbour, flags[1] by the high one.  A wait that lasts longer than `timeout_ns` gives
+// up and raises error bit 32 (a peer that failed must not hang this GPU).
+__global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, volatile unsigned long long *my_flags,
+                                   unsigned long long value, unsigned long long timeout_ns, int *error_flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __threadfence_system();
+  if (peer_lo_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_lo_flag), "l"(value) : "memory");
+  if (peer_hi_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_hi_flag), "l"(value) : "memory");
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? peer_lo_flag : peer_hi_flag)) continue;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"((const unsigned long long *)(my_flags + side)) : "memory");
+      if (v >= value) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        atomicOr(error_flags, 32);
+        return;
+      }
+    }
   }
 }
 

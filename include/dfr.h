@@ -128,7 +128,9 @@ int dfr_set_init_v_omega(dfr_context *ctx, int body, const double v0[3], const d
 int dfr_slab_plan(double z_origin, double inv_cell, int nz, int reach, int64_t n, const double *z, int n_ranks, int32_t *planes);
 int dfr_slab_unique_id(char out[DFR_SLAB_ID_BYTES]);
 int dfr_slab_configure(dfr_context *ctx, int rank, int n_ranks, const char id_bytes[DFR_SLAB_ID_BYTES]);
-/* out = { fluid particles owned, ghost particles held, bytes exchanged over NVLink since reset, number of slabs } */
+/* out = { fluid particles owned, ghost particles held, bytes exchanged over NVLink since reset, number of slabs -
+ * negated when the ghost updates travel as stores from the producing kernels into cudaIpc-mapped neighbour memory
+ * (default; DFR_SLAB_TRANSPORT=nccl or a failed mapping selects NCCL send/recv) } */
 int dfr_slab_info(dfr_context *ctx, int64_t out[4]);
 
 /* Ends scene construction: uploads everything, computes the Akinci boundary volumes

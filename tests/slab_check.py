@@ -92,7 +92,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi)
     si = slab.slab_info()
-    print(f"rank {rank}: owned {si['owned']} ghosts {si['ghosts']} exchanged {si['exchanged_bytes'] / 1e6:.1f} MB over {steps - steps // 2} steps; worst rel diff {worst:.2e}", flush=True)
+    print(f"rank {rank}: owned {si['owned']} ghosts {si['ghosts']} exchanged {si['exchanged_bytes'] / 1e6:.1f} MB ({si['transport']}) over {steps - steps // 2} steps; worst rel diff {worst:.2e}", flush=True)
     dist.barrier()
     if rank == 0:
         print("SLAB_CHECK_OK", flush=True)
