@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 
 #include "scene_host.hpp"
+#include "state_io.hpp"
 
 namespace dfrhost {
 
@@ -301,6 +302,32 @@ class SimulatorBase {
   // mode: 0 full state (loadState), 1 positions only (--load-fluid-pos), 2 positions and velocities
   void loadStateFile(const std::string &path, int mode) {
     deferredInit();
+    const bool own = path.size() > 5 && path.substr(path.size() - 5) == ".dfrs";
+    if (!own) {  // the reference's pair state_<n>.bin + state_<n>_particle_Fluid.bgeo (or a .bgeo given directly)
+      const bool direct = path.size() > 5 && path.substr(path.size() - 5) == ".bgeo";
+      const std::string bgeo = direct ? path : bgeo_of_state_file(path);
+      std::ifstream probe(bgeo, std::ios::binary);
+      if (!probe) {
+        std::fprintf(stderr, "[warn] File %s does not exist; state unchanged\n", bgeo.c_str());
+        return;
+      }
+      probe.close();
+      FluidStateFile st = read_bgeo(bgeo);
+      if (st.n != dfr_num_fluid(ctx)) throw std::runtime_error(bgeo + ": particle count differs from the scene's fluid");
+      // readFluidParticlesState fills every field the file has (positions, velocities, kappa, kappa_v, ...);
+      // --load-fluid-pos then clears the velocities (SimulatorBase.cpp:2043-2058).  Rigid body and parameter state of
+      // the .bin file are not read.
+      std::vector<double> zero;
+      const double *v = st.v.empty() ? nullptr : st.v.data();
+      if (mode == 1) {
+        zero.assign(3 * (size_t)st.n, 0.0);
+        v = zero.data();
+      }
+      check(dfr_load_fluid_state(ctx, st.x.data(), v, st.kappa.empty() ? nullptr : st.kappa.data(), st.kappa_v.empty() ? nullptr : st.kappa_v.data()));
+      info_valid = false;
+      step_serial++;
+      return;
+    }
     std::FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) {  // the reference logs a warning and carries on (SimulatorBase.cpp:2547-2558)
       std::fprintf(stderr, "[warn] state file %s not found; state unchanged\n", path.c_str());

@@ -260,6 +260,37 @@ PYBIND11_MODULE(_core, m) {
       .def_static("printTimeSums", []() {})
       .def_static("reset", []() {});
 
+  // partio .bgeo fluid state files (host/state_io.hpp), exposed for tests and for exporting settled states
+  m.def("_read_bgeo", [](const std::string &path) {
+    FluidStateFile st = read_bgeo(path);
+    py::dict d;
+    auto arr = [](const std::vector<double> &v, py::ssize_t cols) {
+      if (cols > 1) {
+        py::array_t<double> a({(py::ssize_t)(v.size() / cols), cols});
+        std::copy(v.begin(), v.end(), a.mutable_data());
+        return a;
+      }
+      py::array_t<double> a((py::ssize_t)v.size());
+      std::copy(v.begin(), v.end(), a.mutable_data());
+      return a;
+    };
+    d["n"] = st.n;
+    d["x"] = arr(st.x, 3);
+    if (!st.v.empty()) d["v"] = arr(st.v, 3);
+    if (!st.kappa.empty()) d["kappa"] = arr(st.kappa, 1);
+    if (!st.kappa_v.empty()) d["kappa_v"] = arr(st.kappa_v, 1);
+    return d;
+  });
+  m.def("_write_bgeo", [](const std::string &path, py::array_t<double, py::array::c_style | py::array::forcecast> x,
+                           py::array_t<double, py::array::c_style | py::array::forcecast> v,
+                           py::array_t<double, py::array::c_style | py::array::forcecast> kappa,
+                           py::array_t<double, py::array::c_style | py::array::forcecast> kappa_v) {
+    const int64_t n = x.size() / 3;
+    if (v.size() != 3 * n || kappa.size() != n || kappa_v.size() != n) throw py::value_error("array sizes");
+    write_bgeo(path, n, x.data(), v.data(), kappa.data(), kappa_v.data());
+  });
+  m.def("_bgeo_of_state_file", &bgeo_of_state_file);
+
   // scene-side helpers exposed for tests (host logic runs without a GPU)
   m.def("_load_scene_summary", [](const std::string &file, const std::string &param) {
     Scene sc = load_scene(file, param);

@@ -124,3 +124,39 @@ def test_new_init_velocity_changes_the_trajectory_and_state_files_round_trip(tmp
     ts.reset_gradient()
     assert np.array_equal(bm.get_grad_v_to_v0(), np.eye(3)) and not bm.get_grad_x_to_v0().any()
     base.cleanup()
+
+
+def test_state_file_in_the_reference_format(tmp_path):
+    """--state state_3.bin --load-fluid-pos: positions (and kappa) come from state_3_particle_Fluid.bgeo, velocities are
+    cleared, and every reset() re-applies the state (SimulatorBase.cpp:887-934, 1052-1070, 2043-2058)."""
+    sph = import_sph()
+    path = write_scene(tmp_path, target_time=0.01)
+    n = sph._load_scene_summary(path)["num_fluid"]
+    base0 = sph.Exec.SimulatorBase()
+    base0.init(sceneFile=path, useGui=False, outputDir=str(tmp_path / "o0"), stopAt=100.0)
+    base0.initSimulationWithDeferredInit()
+    base0.forwardFixedSteps(3)  # a slightly settled state to store
+    sfile = base0.saveState(str(tmp_path / "st"))
+    base0.cleanup()
+    import struct
+
+    raw = open(sfile, "rb").read()
+    nn, = struct.unpack("<q", raw[8:16])
+    assert nn == n
+    arr = np.frombuffer(raw[24:], dtype=np.float64)
+    x, v = arr[:3 * n].reshape(n, 3), arr[3 * n:6 * n].reshape(n, 3)
+    kap, kapv = arr[6 * n:7 * n], arr[7 * n:8 * n]
+    sph._write_bgeo(str(tmp_path / "st" / "state_3_particle_Fluid.bgeo"), x, v, kap, kapv)
+    (tmp_path / "st" / "state_3.bin").write_bytes(b"")  # the reference's parameter / boundary blob is not read
+    base = sph.Exec.SimulatorBase()
+    base.init(sceneFile=path, useGui=False, outputDir=str(tmp_path / "o1"), stopAt=100.0, stateFile=str(tmp_path / "st" / "state_3.bin"),
+              loadFluidPos=True)
+    base.initSimulationWithDeferredInit()
+    ts = sph.Simulation.getCurrent().getTimeStep()
+    bm = ts.get_boundary_model(1)
+    base.runNewTrajectory()
+    a = (bm.get_position_rb(), bm.get_grad_x_to_v0(), ts.get_step_count())
+    base.runNewTrajectory()  # reset() inside: same stored state again
+    b = (bm.get_position_rb(), bm.get_grad_x_to_v0(), ts.get_step_count())
+    assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    base.cleanup()
