@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -194,6 +195,10 @@ int fail(dfr_context *c, int code, const std::string &msg) {
   } while (0)
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline bool getenv_flag(const char *name) {
+  const char *v = std::getenv(name);
+  return v && *v && *v != '0';
+}
 cudaEvent_t prof_event(dfr_context *c) {
   if (!c->prof_pool.empty()) {
     cudaEvent_t e = c->prof_pool.back();
@@ -755,25 +760,48 @@ void launch_boundary_side(dfr_context *c, bool grad, int iter_kernel) {
 // divergenceSolve / pressureSolve (TimeStepDiffDFSPH.cpp:770-881 / 654-768).  Iterations are enqueued
 // speculatively; every iteration kernel exits at once when the on-device residual test has closed the
 // solve, and the host looks at the flag only after the speculated batch.
+// fuse_density / fuse_normals (divergence solve with warm start only): the first two k_rho launches of the step also do
+// the work of k_density_factor and k_normals (dfr_kernels.cuh: RhoExtra)
 template <bool PRESSURE>
-int launch_solver(dfr_context *c) {
+int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals = false) {
   const int n = c->launch_nf, g = cdiv(n, 128);
   const int a = c->cur;
   const bool warm = PRESSURE ? c->cfg.use_pressure_warmstart : c->cfg.use_divergence_warmstart;
   double *kap = PRESSURE ? c->kappa[a].p : c->kappav[a].p;
-#define RHO_ARGS                                                                                                             \
-  c->P, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
-      c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p, ghost_out(c, GA_XK)
+  RhoExtra X0;
+  std::memset(&X0, 0, sizeof(X0));
+#define RHO_ARGS_X(POS, EXTRA)                                                                                          \
+  c->P, c->dSt.p, (POS), c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c), c->density.p, c->factor.p, \
+      c->pstate[a].p, kap, c->dadv.p, c->xk.p, c->partials.p, ghost_out(c, GA_XK), (EXTRA)
+#define RHO_ARGS RHO_ARGS_X(c->pos[a].p, X0)
 #define PUSH_ARGS \
   c->P, c->dSt.p, c->xk.p, c->vel[c->vcur].p, c->bpos.p, list_f(c), list_b(c), c->pstate[a].p, kap, warm ? 1 : 0, ghost_out(c, GA_VEL0 + c->vcur)
   if (warm) {
-    PLAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, RHO_ARGS);
+    if (!PRESSURE && fuse_density) {
+      RhoExtra X = X0;
+      X.density = c->density.p;
+      X.factor = c->factor.p;
+      X.sgp = c->sgp.p;
+      X.xrho = c->xrho.p;
+      X.go = ghost_out(c, GA_XRHO);
+      PLAUNCH(c, (k_rho<false, RHO_WARM, RHO_X_DENSITY>), g, RHO_ARGS_X(c->pos[a].p, X));
+      // peer stores: the flag of the xk update below also covers the (x, rho) rows
+      if (!c->slab.p2p) SLAB_SYNC(c, c->xrho.p, sizeof(double4));
+    } else
+      PLAUNCH(c, (k_rho<PRESSURE, RHO_WARM>), g, RHO_ARGS);
     SLAB_SYNC(c, c->xk.p, sizeof(double4));
     launch_boundary_side<PRESSURE>(c, false, 0);
     PLAUNCH(c, (k_push<PRESSURE, false>), g, PUSH_ARGS);
     SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
   }
-  PLAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, RHO_ARGS);
+  if (!PRESSURE && warm && fuse_normals) {
+    RhoExtra X = X0;
+    X.normal = c->normal.p;
+    X.go = ghost_out(c, GA_NORMAL);
+    PLAUNCH(c, (k_rho<false, RHO_PLAIN, RHO_X_NORMALS>), g, RHO_ARGS_X(c->xrho.p, X));  // (x, rho) records stand in for x
+    if (!c->slab.p2p) SLAB_SYNC(c, c->normal.p, sizeof(double4));
+  } else
+    PLAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, RHO_ARGS);
   SLAB_SYNC(c, c->xk.p, sizeof(double4));
   const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
   int launched = 0;
@@ -903,18 +931,23 @@ int launch_step(dfr_context *c) {
   n = c->launch_nf;  // slab mode: the number of local particles changes with every exchange
   g = cdiv(n, 128);
   int a = c->cur;
-  PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
-         c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
-  // x|rho is first gathered by k_normals / k_nonpressure: with peer stores any later flag (the divergence solve has
-  // several) covers it
-  if (!(c->slab.p2p && c->cfg.enable_divergence_solver)) SLAB_SYNC(c, c->xrho.p, sizeof(double4));
+  // with the divergence solve and its warm start on, density/factor and the normals ride on the first two k_rho passes
+  const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && !getenv_flag("DFR_NO_FUSION");
+  const bool fuse_normals = fuse && c->cfg.surface_tension_method == 2;
+  if (!fuse) {
+    PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
+           c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
+    // x|rho is first gathered by k_normals / k_nonpressure: with peer stores any later flag (the divergence solve has
+    // several) covers it
+    if (!(c->slab.p2p && c->cfg.enable_divergence_solver)) SLAB_SYNC(c, c->xrho.p, sizeof(double4));
+  }
   bool scale_kv = false;
   if (c->cfg.enable_divergence_solver) {
-    rc = launch_solver<false>(c);
+    rc = launch_solver<false>(c, fuse, fuse_normals);
     if (rc) return rc;
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
-  if (c->cfg.surface_tension_method == 2)
+  if (c->cfg.surface_tension_method == 2 && !fuse_normals)
   {
     PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p, ghost_out(c, GA_NORMAL));
     SLAB_SYNC(c, c->normal.p, sizeof(double4));

@@ -639,12 +639,24 @@ __global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ 
 // TimeStepDiffDFSPH.cpp:1926-2041, 964-999, 1698-1732, 1203-1216, 1906-1915, 711-743, 828-861
 // ---------------------------------------------------------------------------------------------
 enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
+// Passes fused into the first two k_rho launches of a step (divergence solve with warm start; the gathers are the
+// same, so a fused pass costs FP64 work but no extra trip through the neighbour lists):
+//   RHO_X_DENSITY  the first launch also computes density, DFSPH factor, sum V gradW and the (x, rho) record
+//                  (k_density_factor is then not launched)
+//   RHO_X_NORMALS  the second launch gathers (x, rho) instead of x and also computes the surface-tension normals
+//                  (k_normals is then not launched); positions and densities do not change during the solve
+enum { RHO_X_NONE = 0, RHO_X_DENSITY = 1, RHO_X_NORMALS = 2 };
+struct RhoExtra {
+  double *density, *factor;
+  double4 *sgp, *xrho, *normal;
+  GhostOut go;  // ghost rows of the extra gathered array (xrho or normal)
+};
 
-template <bool PRESSURE, int MODE>
-__global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+template <bool PRESSURE, int MODE, int EXTRA = RHO_X_NONE>
+__global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4)) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
                                               const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const GhostOut GO,
-                                              const VSched S) {
+                                              const RhoExtra X, const VSched S) {
   vsched_prologue(S);
   if (MODE == RHO_ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
@@ -658,13 +670,26 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
   if (i >= st->own_begin && i < st->own_end) {
     const double4 pi = pos[i];
     const double4 vi = vel[i];
-      double delta = 0.0;
+    double delta = 0.0;
+    // fused extras
+    double dens = P.volume * P.W_zero, Ssum = 0.0;
+    d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij (RHO_X_DENSITY) / normal sum (RHO_X_NORMALS)
     const int nF = lf.cnt[i];
     for_neighbors4<DFR_RHO_U>(
         lf, i, i, [&](int j) { return Rec2{ldg4(pos + j), ldg4(vel + j)}; },
         [&](const Rec2 &q, int) {
           const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
-          const double c = cubic_grad_coeff(P, dot(r, r));
+          double c;
+          if (EXTRA == RHO_X_DENSITY) {
+            const double wv = cubic_W_and_grad(P, dot(r, r), c);
+            dens += P.volume * wv;
+            const d3 g = (P.volume * c) * r;
+            Ssum += dot(g, g);
+            G += g;
+          } else {
+            c = cubic_grad_coeff(P, dot(r, r));
+            if (EXTRA == RHO_X_NORMALS) G += (P.mass / q.a.w * c) * r;  // pos == xrho here: w is the neighbour's density
+          }
           delta += (P.volume * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
         });
     const int nB = lb.cnt[i];
@@ -672,12 +697,34 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
         lb, i, 0, [&](int j) { return Rec2{ldg4(bpos + j), ldg4(bvel + j)}; },
         [&](const Rec2 &q, int) {
           const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
-          const double c = cubic_grad_coeff(P, dot(r, r));
+          double c;
+          if (EXTRA == RHO_X_DENSITY) {
+            const double wv = cubic_W_and_grad(P, dot(r, r), c);
+            dens += q.a.w * wv;
+            G += (q.a.w * c) * r;
+          } else
+            c = cubic_grad_coeff(P, dot(r, r));
           delta += (q.a.w * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
         });
+    double alpha_i = 0.0;
+    if (EXTRA == RHO_X_DENSITY) {  // k_density_factor's epilogue
+      X.density[i] = dens * P.density0;
+      stg4(X.xrho + i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
+      ghost_store(X.go, i, make_double4(pi.x, pi.y, pi.z, dens * P.density0));
+      const double denom = Ssum + dot(G, G);
+      alpha_i = (denom > DFR_EPS) ? -1.0 / denom : 0.0;
+      X.factor[i] = alpha_i;
+      X.sgp[i] = make_double4(-G.x, -G.y, -G.z, 0.0);
+    } else if (MODE != RHO_WARM)
+      alpha_i = factor[i];
+    if (EXTRA == RHO_X_NORMALS) {  // k_normals' epilogue
+      const double4 nrec = make_double4(P.support_radius * G.x, P.support_radius * G.y, P.support_radius * G.z, pi.w);
+      stg4(X.normal + i, nrec);
+      ghost_store(X.go, i, nrec);
+    }
     double rho;
     if (PRESSURE) {
-      rho = fmax(density[i] / P.density0 + h * delta, 1.0);
+      rho = fmax(density[i] / P.density0 + h * delta, 1.0);  // (the pressure solve never carries an extra)
       err = P.density0 * rho - P.density0;
     } else {
       rho = fmax(delta, 0.0);
@@ -697,7 +744,7 @@ __global__ void __launch_bounds__(128, DFR_RHO_BLOCKS) k_rho(const __grid_consta
       ghost_store(GO, i, make_double4(pi.x, pi.y, pi.z, kap));
     } else {
       const double b = PRESSURE ? rho - 1.0 : rho;
-      const double ks = PRESSURE ? b * factor[i] / (h * h) : b * factor[i] / h;
+      const double ks = PRESSURE ? b * alpha_i / (h * h) : b * alpha_i / h;
       // (x, k) record: the push and the boundary-side kernel gather position and stiffness together
       stg4(xk + i, make_double4(pi.x, pi.y, pi.z, ks));
       ghost_store(GO, i, make_double4(pi.x, pi.y, pi.z, ks));
