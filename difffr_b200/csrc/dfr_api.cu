@@ -195,9 +195,9 @@ int fail(dfr_context *c, int code, const std::string &msg) {
   } while (0)
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
-inline bool getenv_flag(const char *name) {
+inline int getenv_int(const char *name) {
   const char *v = std::getenv(name);
-  return v && *v && *v != '0';
+  return (v && *v) ? std::atoi(v) : 0;
 }
 cudaEvent_t prof_event(dfr_context *c) {
   if (!c->prof_pool.empty()) {
@@ -762,8 +762,11 @@ void launch_boundary_side(dfr_context *c, bool grad, int iter_kernel) {
 // solve, and the host looks at the flag only after the speculated batch.
 // fuse_density / fuse_normals (divergence solve with warm start only): the first two k_rho launches of the step also do
 // the work of k_density_factor and k_normals (dfr_kernels.cuh: RhoExtra)
+// fuse_nonpressure: the last launch of the first speculated batch of iterations also evaluates the non-pressure
+// accelerations; *nonpressure_done tells whether that launch really was the last active iteration.
 template <bool PRESSURE>
-int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals = false) {
+int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals = false, bool fuse_nonpressure = false,
+                  bool *nonpressure_done = nullptr) {
   const int n = c->launch_nf, g = cdiv(n, 128);
   const int a = c->cur;
   const bool warm = PRESSURE ? c->cfg.use_pressure_warmstart : c->cfg.use_divergence_warmstart;
@@ -806,6 +809,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
   const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
   int launched = 0;
   int spec = PRESSURE ? c->spec_prs : c->spec_div;
+  int fused_at = -1;  // iteration count at which the fused non-pressure pass ran
   for (;;) {
     spec = std::max(1, std::min(spec, max_it - launched));
     for (int it = 0; it < spec; it++) {
@@ -814,7 +818,14 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
       launch_boundary_side<PRESSURE>(c, true, 1);
       PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
       SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
-      PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
+      if (!PRESSURE && fuse_nonpressure && launched == 0 && it == spec - 1) {
+        RhoExtra X = X0;
+        X.normal = c->normal.p;
+        X.acc = c->acc.p;
+        PLAUNCH(c, (k_rho<false, RHO_ITER, RHO_X_NONPRESSURE>), g, RHO_ARGS_X(c->xrho.p, X));
+        fused_at = spec;
+      } else
+        PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
       if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
@@ -835,6 +846,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
     spec = 1;
   }
   const int used = PRESSURE ? c->hSt->prs_iters : c->hSt->div_iters;
+  if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at);
   if (PRESSURE)
     c->spec_prs = std::max(used, c->cfg.min_iterations);
   else
@@ -931,9 +943,12 @@ int launch_step(dfr_context *c) {
   n = c->launch_nf;  // slab mode: the number of local particles changes with every exchange
   g = cdiv(n, 128);
   int a = c->cur;
-  // with the divergence solve and its warm start on, density/factor and the normals ride on the first two k_rho passes
-  const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && !getenv_flag("DFR_NO_FUSION");
+  // with the divergence solve and its warm start on, density/factor, the normals and the non-pressure accelerations ride
+  // on k_rho passes of that solve (dfr_kernels.cuh: RhoExtra); DFR_NO_FUSION=1 switches all of it off, =2 only the last
+  const int no_fusion = getenv_int("DFR_NO_FUSION");
+  const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && no_fusion != 1;
   const bool fuse_normals = fuse && c->cfg.surface_tension_method == 2;
+  const bool fuse_nonpressure = fuse && no_fusion != 2;
   if (!fuse) {
     PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
            c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
@@ -941,9 +956,9 @@ int launch_step(dfr_context *c) {
     // several) covers it
     if (!(c->slab.p2p && c->cfg.enable_divergence_solver)) SLAB_SYNC(c, c->xrho.p, sizeof(double4));
   }
-  bool scale_kv = false;
+  bool scale_kv = false, nonpressure_done = false;
   if (c->cfg.enable_divergence_solver) {
-    rc = launch_solver<false>(c, fuse, fuse_normals);
+    rc = launch_solver<false>(c, fuse, fuse_normals, fuse_nonpressure, &nonpressure_done);
     if (rc) return rc;
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
@@ -952,9 +967,13 @@ int launch_step(dfr_context *c) {
     PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p, ghost_out(c, GA_NORMAL));
     SLAB_SYNC(c, c->normal.p, sizeof(double4));
   }
-  PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
-         c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p,
-         ghost_out(c, GA_VEL0 + (1 - c->vcur)));
+  if (nonpressure_done)
+    LAUNCH(c, k_apply_accel, g, 128, c->dSt.p, c->acc.p, c->vel[c->vcur].p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0,
+           c->vel[1 - c->vcur].p, ghost_out(c, GA_VEL0 + (1 - c->vcur)));
+  else
+    PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+           c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p,
+           ghost_out(c, GA_VEL0 + (1 - c->vcur)));
   c->vcur = 1 - c->vcur;
   if (!c->slab.p2p) SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));  // peer stores: ordered by the CFL all-reduce below
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);

@@ -645,12 +645,30 @@ enum { RHO_PLAIN = 0, RHO_WARM = 1, RHO_ITER = 2 };
 //                  (k_density_factor is then not launched)
 //   RHO_X_NORMALS  the second launch gathers (x, rho) instead of x and also computes the surface-tension normals
 //                  (k_normals is then not launched); positions and densities do not change during the solve
-enum { RHO_X_NONE = 0, RHO_X_DENSITY = 1, RHO_X_NORMALS = 2 };
+//   RHO_X_NONPRESSURE  an iteration launch also evaluates the non-pressure accelerations (surface tension + viscosity,
+//                  k_nonpressure's pair loop: it gathers (x, rho), v and the normal) into `acc`.  The result is only
+//                  valid if that launch turns out to be the LAST active iteration of the divergence solve (its input
+//                  velocities are then the final ones); the host checks the iteration count and otherwise runs
+//                  k_nonpressure.  k_apply_accel then does v += h a, the CFL maximum and the kappa_v rescale.
+enum { RHO_X_NONE = 0, RHO_X_DENSITY = 1, RHO_X_NORMALS = 2, RHO_X_NONPRESSURE = 3 };
 struct RhoExtra {
   double *density, *factor;
-  double4 *sgp, *xrho, *normal;
+  double4 *sgp, *xrho, *normal, *acc;
   GhostOut go;  // ghost rows of the extra gathered array (xrho or normal)
 };
+// pair terms of SurfaceTension_Akinci2013::step (SurfaceTension_Akinci2013.cpp:60-151) and Viscosity_Standard::step
+// (Viscosity_Standard.cpp:233-334) for one fluid neighbour; r = x_i - x_j, c the cubic gradient coefficient
+__device__ __forceinline__ void nonpressure_pair(const Params &P, bool st_on, bool visc_on, const d3 &r, double r2, double c, double rhoi,
+                                                 double rhoj, const d3 &ni, const double4 &nj, double vdotr, double h2s, d3 &a) {
+  if (st_on) {
+    const double K_ij = 2.0 * P.density0 / (rhoi + rhoj);
+    d3 accel = mk3(0, 0, 0);
+    if (r2 > 1.0e-9) accel -= (P.surface_tension * P.mass * cohesion_W(P, r2) * rsqrt(r2)) * r;
+    accel -= P.surface_tension * mk3(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z);
+    a += K_ij * accel;
+  }
+  if (visc_on) a += (10.0 * P.viscosity * (P.mass / rhoj) * vdotr / (r2 + 0.01 * h2s) * c) * r;
+}
 
 template <bool PRESSURE, int MODE, int EXTRA = RHO_X_NONE>
 __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4)) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
@@ -675,6 +693,34 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4
     double dens = P.volume * P.W_zero, Ssum = 0.0;
     d3 G = mk3(0, 0, 0);  // sum_j V_j gradW_ij (RHO_X_DENSITY) / normal sum (RHO_X_NORMALS)
     const int nF = lf.cnt[i];
+    // RHO_X_NONPRESSURE state (pos == xrho: pi.w is the particle's density)
+    const bool st_on = (EXTRA == RHO_X_NONPRESSURE) && P.st_method == 2;
+    const bool visc_on = (EXTRA == RHO_X_NONPRESSURE) && P.visc_method == 1;
+    const double h2s = P.support_radius * P.support_radius;
+    d3 ni = mk3(0, 0, 0), acc = mk3(0, 0, 0);
+    if (EXTRA == RHO_X_NONPRESSURE) {
+      if (st_on) {
+        const double4 n4 = X.normal[i];
+        ni = mk3(n4.x, n4.y, n4.z);
+      }
+      for_neighbors4<DFR_NP_U>(
+          lf, i, i,
+          [&](int j) {
+            Rec3 q;
+            q.a = ldg4(pos + j);
+            q.b = ldg4(vel + j);
+            if (st_on) q.c = ldg4(X.normal + j);
+            return q;
+          },
+          [&](const Rec3 &q, int) {
+            const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
+            const double r2 = dot(r, r);
+            const double c = cubic_grad_coeff(P, r2);
+            const double vdotr = (vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z;
+            delta += (P.volume * c) * vdotr;
+            nonpressure_pair(P, st_on, visc_on, r, r2, c, pi.w, q.a.w, ni, q.c, vdotr, h2s, acc);
+          });
+    } else
     for_neighbors4<DFR_RHO_U>(
         lf, i, i, [&](int j) { return Rec2{ldg4(pos + j), ldg4(vel + j)}; },
         [&](const Rec2 &q, int) {
@@ -704,8 +750,17 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4
             G += (q.a.w * c) * r;
           } else
             c = cubic_grad_coeff(P, dot(r, r));
-          delta += (q.a.w * c) * ((vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z);
+          const double vdotr = (vi.x - q.b.x) * r.x + (vi.y - q.b.y) * r.y + (vi.z - q.b.z) * r.z;
+          delta += (q.a.w * c) * vdotr;
+          if (EXTRA == RHO_X_NONPRESSURE) {  // boundary adhesion / boundary viscosity (zero coefficients in every shipped scene)
+            const double r2 = dot(r, r);
+            if (st_on && P.surface_tension_b != 0.0 && r2 > 1.0e-9)
+              acc -= (P.surface_tension_b * P.density0 * q.a.w * adhesion_W(P, r2) * rsqrt(r2)) * r;
+            if (visc_on && P.viscosity_b != 0.0)
+              acc += (10.0 * P.viscosity_b * (P.density0 * q.a.w / pi.w) * vdotr / (r2 + 0.01 * h2s) * c) * r;
+          }
         });
+    if (EXTRA == RHO_X_NONPRESSURE) X.acc[i] = make_double4(P.gx + acc.x, P.gy + acc.y, P.gz + acc.z, 0.0);
     double alpha_i = 0.0;
     if (EXTRA == RHO_X_DENSITY) {  // k_density_factor's epilogue
       X.density[i] = dens * P.density0;
@@ -1122,19 +1177,12 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
         [&](const Rec3 &q, int) {
           const d3 r = mk3(pi.x - q.a.x, pi.y - q.a.y, pi.z - q.a.z);
           const double r2 = dot(r, r);
-          const double rhoj = q.a.w;
-          if (st_on) {
-            const double K_ij = 2.0 * P.density0 / (rhoi + rhoj);
-            d3 accel = mk3(0, 0, 0);
-            if (r2 > 1.0e-9) accel -= (P.surface_tension * P.mass * cohesion_W(P, r2) * rsqrt(r2)) * r;
-            accel -= P.surface_tension * mk3(ni.x - q.b.x, ni.y - q.b.y, ni.z - q.b.z);
-            a += K_ij * accel;
-          }
+          double c = 0.0, vdotr = 0.0;
           if (visc_on) {
-            const double c = cubic_grad_coeff(P, r2);
-            const double vx = (vi.x - q.c.x) * r.x + (vi.y - q.c.y) * r.y + (vi.z - q.c.z) * r.z;
-            a += (10.0 * P.viscosity * (P.mass / rhoj) * vx / (r2 + 0.01 * h2s) * c) * r;
+            c = cubic_grad_coeff(P, r2);
+            vdotr = (vi.x - q.c.x) * r.x + (vi.y - q.c.y) * r.y + (vi.z - q.c.z) * r.z;
           }
+          nonpressure_pair(P, st_on, visc_on, r, r2, c, rhoi, q.a.w, ni, q.b, vdotr, h2s, a);
         });
     if ((st_on && P.surface_tension_b != 0.0) || (visc_on && P.viscosity_b != 0.0)) {
       // boundary adhesion / boundary viscosity: zero coefficients in every shipped scene; the
@@ -1170,6 +1218,34 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
     const double m = fmax(fmax(wmax[0], wmax[1]), fmax(wmax[2], wmax[3]));
     atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(m));
   }
+  }
+}
+
+// v += h a, CFL maximum and kappa_v rescale for accelerations that a fused k_rho pass wrote (RHO_X_NONPRESSURE):
+// the tail of k_nonpressure as a streaming pass (TimeStepDiffDFSPH.cpp:589-604, Simulation.cpp:542-575)
+__global__ void __launch_bounds__(128) k_apply_accel(StepState *st, const double4 *acc, const double4 *vel, const int *state, double *kappav,
+                                                      int scale_kappav, double4 *vel_out, const GhostOut GO) {
+  const double h = st->h_step;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  double mag = 0.0;
+  if (i >= st->own_begin && i < st->own_end) {
+    const double4 a = acc[i];
+    const double4 vi = vel[i];
+    const d3 vn = mk3(vi.x + h * a.x, vi.y + h * a.y, vi.z + h * a.z);
+    mag = dot(vn, vn);
+    const double4 vo = (state[i] == 0) ? make_double4(vn.x, vn.y, vn.z, 0.0) : vi;
+    vel_out[i] = vo;
+    ghost_store(GO, i, vo);
+    if (scale_kappav) kappav[i] *= h;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mag = fmax(mag, __shfl_xor_sync(DFR_FULL, mag, o));
+  __shared__ double wmax[4];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double m = fmax(fmax(wmax[0], wmax[1]), fmax(wmax[2], wmax[3]));
+    atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(m));
   }
 }
 

@@ -12,8 +12,14 @@ sc = scenes.dam_break_scene(n, n_boxes=bench.N_BOXES)
 ctx = scenes.build_context(lambda **k: Context(device=0, **k), sc, **bench.CFG)
 ctx.step(warm)
 ms0, _ = ctx.device_time_ms()
+i0 = ctx.step_info()
 ctx.step(steps)
 ms1, _ = ctx.device_time_ms()
+i1 = ctx.step_info()
+ps = max(i1.total_particle_steps - i0.total_particle_steps, 1)
+stats = (f"D {(i1.total_divergence_iterations - i0.total_divergence_iterations) / steps:.2f} "
+         f"P {(i1.total_pressure_iterations - i0.total_pressure_iterations) / steps:.2f} "
+         f"nbrs {(i1.total_fluid_neighbors - i0.total_fluid_neighbors) / ps:.1f} h {i1.time_step_size:.2e}")
 ctx.set_profiling(True)
 ctx.step(5)
 prof = ctx.kernel_profile()
@@ -25,4 +31,4 @@ for k, (ms, cnt) in prof.items():
     a = cls.setdefault(b, [0.0, 0])
     a[0] += ms; a[1] += cnt
 top = sorted(cls.items(), key=lambda kv: -kv[1][0])[:7]
-print(os.environ.get("DFR_LIBRARY", "default"), f"ms/step {(ms1-ms0)/steps:.3f} |", " ".join(f"{k}:{v[0]/v[1]*1e3:.0f}us" for k, v in top))
+print(os.environ.get("DFR_LIBRARY", "default"), f"ms/step {(ms1-ms0)/steps:.3f} {stats} |", " ".join(f"{k}:{v[0]/v[1]*1e3:.0f}us" for k, v in top))
