@@ -3,9 +3,12 @@
 // from shared memory.  Prints SM cycles per warp-gather (all SMs busy, many warps per SM).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_probe gather_probe.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
-#define NREC 2048  // 64 KB table
+#define NREC_SMALL 2048  // 64 KB table: L1 resident
+__constant__ unsigned int c_nrec = NREC_SMALL;  // records in the table (power of two)
+#define NREC c_nrec
 __device__ __forceinline__ unsigned int hash32(unsigned int x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
@@ -48,7 +51,7 @@ template <int P, int W /*0: 256-bit, 1: 2x128-bit, 2: shared 2x LDS.128, 3: 4x64
 __global__ void __launch_bounds__(256) k_probe(const double4 *tab, double *out, int iters) {
   extern __shared__ double4 stab[];
   if (W == 2) {
-    for (int i = threadIdx.x; i < NREC; i += blockDim.x) stab[i] = tab[i];
+    for (int i = threadIdx.x; i < NREC_SMALL; i += blockDim.x) stab[i] = tab[i];
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) k_probe(const double4 *tab, double *out, 
 template <int P, int W>
 void run(const double4 *tab, double *out, int nsm, double mhz) {
   const int iters = 2000, blocks = nsm * 8;
-  const size_t sh = (W == 2) ? NREC * sizeof(double4) : 0;
+  const size_t sh = (W == 2) ? NREC_SMALL * sizeof(double4) : 0;
   if (W == 2) cudaFuncSetAttribute(k_probe<P, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
   const int nb = (W == 2) ? nsm * 3 : blocks;
   k_probe<P, W><<<nb, 256, sh>>>(tab, out, 100);
@@ -109,16 +112,17 @@ void run(const double4 *tab, double *out, int nsm, double mhz) {
   const double cyc = ms * 1e-3 * mhz * 1e6;
   printf("  W%d: %6.2f cyc/gather", W, cyc / gathers_per_sm);
 }
+static bool g_small = true;
 template <int P>
 void row(const char *name, const double4 *tab, double *out, int nsm, double mhz) {
   printf("P%-2d %-52s", P, name);
   run<P, 0>(tab, out, nsm, mhz);
   run<P, 1>(tab, out, nsm, mhz);
   run<P, 3>(tab, out, nsm, mhz);
-  run<P, 2>(tab, out, nsm, mhz);
+  if (g_small) run<P, 2>(tab, out, nsm, mhz);
   printf("\n");
 }
-int main() {
+int main(int argc, char **argv) {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
   int khz = 0;
@@ -126,8 +130,12 @@ int main() {
   const double mhz = khz / 1000.0;
   double4 *tab;
   double *out;
-  cudaMalloc(&tab, NREC * sizeof(double4));
-  cudaMemset(tab, 0, NREC * sizeof(double4));
+  const unsigned int nrec = argc > 1 ? (unsigned int)atoi(argv[1]) : NREC_SMALL;  // e.g. 2097152 = 64 MB: L2 resident, L1 misses
+  cudaMemcpyToSymbol(c_nrec, &nrec, sizeof(nrec));
+  g_small = (nrec == NREC_SMALL);
+  cudaMalloc(&tab, (size_t)nrec * sizeof(double4));
+  cudaMemset(tab, 0, (size_t)nrec * sizeof(double4));
+  printf("table: %u records (%.1f MB)\n", nrec, nrec * 32.0 / 1e6);
   cudaMalloc(&out, 8);
   printf("SMs %d clock %.0f MHz; cycles per warp-wide gather of 32-byte records (W0 LDG.256, W1 2xLDG.128, W3 4xLDG.64, W2 shared 2xLDS.128)\n",
          p.multiProcessorCount, mhz);
