@@ -289,7 +289,7 @@ int scan_u32(dfr_context *c, unsigned int *data, size_t n, unsigned int *total) 
   if ((size_t)ntiles > c->tile_sums.n) return fail(c, DFR_ERR_CAPACITY, "scan scratch too small");
   LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, data, data, c->tile_sums.p, n);
   LAUNCH(c, k_scan_sums, 1, 1024, c->tile_sums.p, ntiles, total);
-  if (ntiles > 1) LAUNCH(c, k_scan_add, cdiv((int64_t)n, 256), 256, data, c->tile_sums.p, n);
+  if (ntiles > 1) LAUNCH(c, k_scan_add, cdiv((int64_t)n, 1024), 256, data, c->tile_sums.p, n);
   return DFR_OK;
 }
 
@@ -383,7 +383,8 @@ int build_dyn_grid(dfr_context *c) {
   if (rc) return rc;
   LAUNCH(c, k_bin_scatter, cdiv(c->n_dyn_p, 128), 128, (const int *)nullptr, c->n_dyn_p, c->cell_start_d.p, c->cell_of_b.p,
          c->rank_b.p, c->sorted_src_d.p);
-  LAUNCH(c, k_bin_sort_cells, cdiv(nc, 128), 128, c->cell_start_d.p, nc, c->sorted_src_d.p);
+  LAUNCH(c, k_bin_sort_cells_by_particle, cdiv(c->n_dyn_p, 128), 128, (const int *)nullptr, c->n_dyn_p, c->cell_start_d.p,
+         c->cell_of_b.p, c->rank_b.p, c->sorted_src_d.p);
   return DFR_OK;
 }
 
@@ -405,7 +406,8 @@ int build_neighbors(dfr_context *c) {
   int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
   if (rc) return rc;
   LAUNCH(c, k_bin_scatter, cdiv(n, 128), 128, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p, c->sorted_src_f.p);
-  LAUNCH(c, k_bin_sort_cells, cdiv(nc, 128), 128, c->cell_start_f.p, nc, c->sorted_src_f.p);
+  LAUNCH(c, k_bin_sort_cells_by_particle, cdiv(n, 128), 128, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
+         c->sorted_src_f.p);
   LAUNCH(c, k_permute_fluid, cdiv(n, 128), 128, c->dSt.p, c->sorted_src_f.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p,
          c->kappav[a].p, c->pid[a].p, c->pstate[a].p, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p, c->kappav[b].p,
          c->pid[b].p, c->pstate[b].p);
@@ -423,10 +425,10 @@ int build_neighbor_lists(dfr_context *c) {
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
-    LAUNCH(c, k_dnbr_count, cdiv(c->n_dyn_p, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
+    LAUNCH(c, k_dnbr_count, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
     rc = scan_u32(c, c->off_d.p, (size_t)c->n_dyn_p + 1, nullptr);
     if (rc) return rc;
-    LAUNCH(c, k_dnbr_fill, cdiv(c->n_dyn_p, 128), 128, c->P, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
+    LAUNCH(c, k_dnbr_fill, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
            c->off_d.p, c->idx_d.p, c->cap_d);
   }
   return DFR_OK;

@@ -17,13 +17,24 @@ namespace dfr {
 #define DFR_PUSH_U 2
 #endif
 #ifndef DFR_NP_U
-#define DFR_NP_U 2
+#define DFR_NP_U 1
 #endif
 #ifndef DFR_DF_U
 #define DFR_DF_U 4
 #endif
 #ifndef DFR_RHO_BLOCKS
 #define DFR_RHO_BLOCKS 8
+#endif
+// resident 128-thread blocks per SM asked of the compiler (register cap = 512 / blocks) for the fused k_rho variants
+// and for k_push
+#ifndef DFR_RHOX_BLOCKS
+#define DFR_RHOX_BLOCKS 7
+#endif
+#ifndef DFR_RHONP_BLOCKS
+#define DFR_RHONP_BLOCKS 5
+#endif
+#ifndef DFR_PUSH_BLOCKS
+#define DFR_PUSH_BLOCKS 8
 #endif
 struct Rec2 {
   double4 a, b;
@@ -282,11 +293,18 @@ __global__ void k_scan_tiles(const unsigned int *in, unsigned int *out, unsigned
   const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
   unsigned int v[SCAN_ITEMS];
   unsigned int sum = 0;
+  static_assert(SCAN_ITEMS == 8, "two 128-bit accesses per thread");
+  const bool full = (base + SCAN_ITEMS <= n);
+  if (full) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = (base + k < n) ? in[base + k] : 0u;
-    sum += v[k];
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0u;
   }
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) sum += v[k];
   // inclusive scan of thread sums
   unsigned int incl = sum;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -310,10 +328,19 @@ __global__ void k_scan_tiles(const unsigned int *in, unsigned int *out, unsigned
   }
   __syncthreads();
   unsigned int run = warp_sums[wid] + (incl - sum);
+  unsigned int o8[SCAN_ITEMS];
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < n) out[base + k] = run;
+    o8[k] = run;
     run += v[k];
+  }
+  if (full) {
+    *reinterpret_cast<uint4 *>(out + base) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+    *reinterpret_cast<uint4 *>(out + base + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+      if (base + k < n) out[base + k] = o8[k];
   }
 }
 // single block: exclusive scan of the tile sums in place; writes the grand total to *total
@@ -354,9 +381,18 @@ __global__ void k_scan_sums(unsigned int *tile_sums, int ntiles, unsigned int *t
   }
   if (threadIdx.x == 0 && total) *total = carry_s;
 }
+// four elements per thread (SCAN_TILE is a multiple of 4, so the four share one tile)
 __global__ void k_scan_add(unsigned int *out, const unsigned int *tile_sums, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const unsigned int add = tile_sums[i / SCAN_TILE];
+  if (i + 4 <= n) {
+    uint4 v = *reinterpret_cast<uint4 *>(out + i);
+    v.x += add; v.y += add; v.z += add; v.w += add;
+    *reinterpret_cast<uint4 *>(out + i) = v;
+  } else {
+    for (size_t k = i; k < n; k++) out[k] += add;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,6 +431,53 @@ __global__ void k_bin_sort_cells(const unsigned int *cell_start, int ncells, int
     for (int i = 1; i < m; i++) {
       const int v = a[i];
       int j = i - 1;
+      while (j >= 0 && a[j] > v) {
+        a[j + 1] = a[j];
+        j--;
+      }
+      a[j + 1] = v;
+    }
+  } else {  // heap sort (edge cells collecting escaped particles)
+    for (int start = m / 2 - 1; start >= 0; start--) {
+      int root = start;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= m) break;
+        if (child + 1 < m && a[child] < a[child + 1]) child++;
+        if (a[root] >= a[child]) break;
+        const int t = a[root]; a[root] = a[child]; a[child] = t;
+        root = child;
+      }
+    }
+    for (int end = m - 1; end > 0; end--) {
+      const int t0 = a[0]; a[0] = a[end]; a[end] = t0;
+      int root = 0;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= end) break;
+        if (child + 1 < end && a[child] < a[child + 1]) child++;
+        if (a[root] >= a[child]) break;
+        const int t = a[root]; a[root] = a[child]; a[child] = t;
+        root = child;
+      }
+    }
+  }
+}
+// Same ordering pass driven from the particles: the particle that drew rank 0 of a cell sorts that cell's slice
+// (one thread per particle instead of one per cell: the grid covers the whole tank, most of its cells are empty)
+__global__ void k_bin_sort_cells_by_particle(const int *n_ptr, int n_fixed, const unsigned int *cell_start, const int *cell_of_particle,
+                                             const int *rank_in_cell, int *sorted_src) {
+  const int n = n_ptr ? *n_ptr : n_fixed;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || rank_in_cell[i] != 0) return;
+  const int c = cell_of_particle[i];
+  const int s = (int)cell_start[c], m = (int)cell_start[c + 1] - s;
+  if (m < 2) return;
+  int *a = sorted_src + s;
+  if (m <= 64) {
+    for (int p = 1; p < m; p++) {
+      const int v = a[p];
+      int j = p - 1;
       while (j >= 0 && a[j] > v) {
         a[j + 1] = a[j];
         j--;
@@ -534,27 +617,78 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
   }
   }
 }
-// dynamic boundary particle -> fluid neighbours, CSR rows (one warp later walks one row)
+// One stencil row of a point in cell (cx, cy, cz): row rr = (z - (cz - R)) * (2R + 1) + (y - (cy - R)), the order in
+// which for_each_in_range walks the rows; [s, e) is the slot range of the row's cells (empty outside the grid).
+__device__ __forceinline__ void stencil_row(const Params &P, const GridView &g, int cx, int cy, int cz, int rr, int &s, int &e) {
+  const int R = P.grid.reach, W = 2 * R + 1;
+  const int z = cz - R + rr / W, y = cy - R + rr % W;
+  s = e = 0;
+  if (z < 0 || z >= P.grid.nz || y < 0 || y >= P.grid.ny) return;
+  const int xlo = max(cx - R, 0), xhi = min(cx + R, P.grid.nx - 1);
+  s = (int)g.cell_start[cell_lin(P.grid, xlo, y, z)];
+  e = (int)g.cell_start[cell_lin(P.grid, xhi, y, z) + 1];
+}
+// dynamic boundary particle -> fluid neighbours, CSR rows (one warp later walks one row).  There are few dynamic
+// boundary particles (hundreds to ~15 k), so one WARP searches for one particle, a lane per stencil row; rows are
+// written in stencil order, i.e. exactly the order a sequential walk produces.
 __global__ void __launch_bounds__(128) k_dnbr_count(const __grid_constant__ Params P, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf, unsigned int *cnt_d) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_dyn) return;
   const double4 p = bpos[dyn_begin + t];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int rows = (2 * P.grid.reach + 1) * (2 * P.grid.reach + 1);
   unsigned int c = 0;
-  for_each_in_range(P, gf, p.x, p.y, p.z, -1, [&](int) { c++; });
-  cnt_d[t] = c;
+  for (int rr = lane; rr < rows; rr += 32) {
+    int s, e;
+    stencil_row(P, gf, cx, cy, cz, rr, s, e);
+    for (int q = s; q < e; q++) {
+      const int j = gf.sorted_src ? gf.sorted_src[q] : q;
+      const double4 x = ldg4(gf.pos + j);
+      if (dist2_exact(p.x, p.y, p.z, x.x, x.y, x.z) < P.r2) c++;
+    }
+  }
+  c = __reduce_add_sync(DFR_FULL, c);
+  if (lane == 0) cnt_d[t] = c;
 }
 __global__ void __launch_bounds__(128) k_dnbr_fill(const __grid_constant__ Params P, StepState *st, const double4 *bpos, int dyn_begin, int n_dyn, GridView gf,
                                                     const unsigned int *off_d, int *idx_d, unsigned int cap_d) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_dyn) return;
   if (off_d[t + 1] > cap_d) {
-    atomicOr(&st->error_flags, 4);
+    if (lane == 0) atomicOr(&st->error_flags, 4);
     return;
   }
-  if (t == 0) st->list_used_d = off_d[n_dyn];
+  if (t == 0 && lane == 0) st->list_used_d = off_d[n_dyn];
   const double4 p = bpos[dyn_begin + t];
-  int *o = idx_d + off_d[t];
-  for_each_in_range(P, gf, p.x, p.y, p.z, -1, [&](int j) { *o++ = j; });
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int rows = (2 * P.grid.reach + 1) * (2 * P.grid.reach + 1);
+  unsigned int base = off_d[t];
+  for (int r0 = 0; r0 < rows; r0 += 32) {
+    const int rr = r0 + lane;
+    int s = 0, e = 0;
+    if (rr < rows) stencil_row(P, gf, cx, cy, cz, rr, s, e);
+    unsigned int m = 0;
+    for (int q = s; q < e; q++) {
+      const int j = gf.sorted_src ? gf.sorted_src[q] : q;
+      const double4 x = ldg4(gf.pos + j);
+      if (dist2_exact(p.x, p.y, p.z, x.x, x.y, x.z) < P.r2) m++;
+    }
+    unsigned int incl = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(DFR_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int *o = idx_d + base + (incl - m);
+    for (int q = s; q < e; q++) {
+      const int j = gf.sorted_src ? gf.sorted_src[q] : q;
+      const double4 x = ldg4(gf.pos + j);
+      if (dist2_exact(p.x, p.y, p.z, x.x, x.y, x.z) < P.r2) *o++ = gf.base + j;
+    }
+    base += __shfl_sync(DFR_FULL, incl, 31);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -671,7 +805,7 @@ __device__ __forceinline__ void nonpressure_pair(const Params &P, bool st_on, bo
 }
 
 template <bool PRESSURE, int MODE, int EXTRA = RHO_X_NONE>
-__global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4)) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (EXTRA == RHO_X_NONPRESSURE ? DFR_RHONP_BLOCKS : DFR_RHOX_BLOCKS))) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
                                               const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const GhostOut GO,
                                               const RhoExtra X, const VSched S) {
@@ -867,7 +1001,7 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : 4
 // (k_boundary_side) instead of being scattered from here.
 // ---------------------------------------------------------------------------------------------
 template <bool PRESSURE, bool ITER>
-__global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(128, DFR_PUSH_BLOCKS) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
                                                NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa,
                                                const GhostOut GO, const VSched S) {
   vsched_prologue(S);
@@ -919,7 +1053,7 @@ __global__ void __launch_bounds__(128) k_push(const __grid_constant__ Params P, 
 // per-warp rows are combined in a fixed order (deterministic FP64 sums).
 // ---------------------------------------------------------------------------------------------
 #define BS_WARPS 4
-#define BS_PART_PER_BLOCK 32  // boundary particles per block (8 per warp)
+#define BS_PART_PER_BLOCK 8  // boundary particles per block (2 per warp): few dynamic particles, so many small blocks
 
 template <int MODE /*0 pressure, 1 divergence*/, bool GRAD>
 __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_constant__ Params P, const StepState *st, const BodyDev *bodies, const int *blk_body,

@@ -32,3 +32,6 @@ for k, (ms, cnt) in prof.items():
     a[0] += ms; a[1] += cnt
 top = sorted(cls.items(), key=lambda kv: -kv[1][0])[:7]
 print(os.environ.get("DFR_LIBRARY", "default"), f"ms/step {(ms1-ms0)/steps:.3f} {stats} |", " ".join(f"{k}:{v[0]/v[1]*1e3:.0f}us" for k, v in top))
+if os.environ.get("DFR_VARIANT_DETAIL"):
+    det = sorted(((k, v) for k, v in prof.items() if not k.endswith("(idle)")), key=lambda kv: -kv[1][0])[:14]
+    print("   detail:", " | ".join(f"{k.strip('()').replace('RHO_', '').replace('false', '0').replace('true', '1')}:{v[0]/v[1]*1e3:.0f}us x{v[1]/5:.0f}" for k, v in det))
