@@ -60,6 +60,22 @@ def kernel_class(name):
     return base
 
 
+def kernel_bytes_per_particle(name, nbar):
+    """Algorithmic bytes per fluid particle of ONE launch of `name` (the profile key, template arguments included)."""
+    fn = KERNEL_BYTES.get(kernel_class(name))
+    if fn is None:
+        return None
+    b = fn(nbar, 0.0)
+    # passes fused into k_rho launches of the divergence solve (dfr_kernels.cuh: RhoExtra)
+    if "X_DENSITY" in name:
+        b += 8 + 8 + 32 + 32          # + density, factor, sum V gradW, (x, rho) written
+    elif "X_NORMALS" in name:
+        b += 32                        # + normal written
+    elif "X_NONPRESSURE" in name:
+        b += 32 + 32                   # + own normal read, acceleration written
+    return b
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -362,11 +378,19 @@ def main():
     total_ms = sum(v[0] for v in classes.values())
     top = max(classes.items(), key=lambda kv: kv[1][0])
     top_name, (top_ms, top_n) = top[0], top[1]
-    nf_mean = nbar  # fluid + boundary neighbours per particle
-    bytes_fn = KERNEL_BYTES.get(top_name)
-    if bytes_fn is not None:
-        top_bytes = bytes_fn(nf_mean, 0.0) * nf_rank
-        achieved = top_bytes / (top_ms / top_n * 1e-3) / 1e9
+    # algorithmic bytes of the launches of that class in the profiled steps, variant by variant
+    top_bytes_total, known = 0.0, True
+    for name, (ms, n) in prof.items():
+        if name.endswith("(idle)") or kernel_class(name) != top_name:
+            continue
+        b = kernel_bytes_per_particle(name, nbar)
+        if b is None:
+            known = False
+            break
+        top_bytes_total += b * nf_rank * n
+    if known and top_n:
+        top_bytes = top_bytes_total / top_n            # mean per launch
+        achieved = top_bytes_total / (top_ms * 1e-3) / 1e9
     else:
         top_bytes, achieved = None, None
     step_bytes = algorithmic_bytes_per_particle_step(nbar, D, P)

@@ -702,7 +702,8 @@ int slab_exchange_and_sort(dfr_context *c) {
   if (rc) return rc;
   LAUNCH(c, k_bin_scatter, cdiv(n_src, 128), 128, (const int *)nullptr, n_src, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
          c->sorted_src_f.p);
-  LAUNCH(c, k_bin_sort_cells_by_id, cdiv(nc, 128), 128, c->cell_start_f.p, nc, c->sorted_src_f.p, c->pid[a].p + own_begin);
+  LAUNCH(c, k_bin_sort_cells_by_id, cdiv(n_src, 128), 128, n_src, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
+         c->sorted_src_f.p, c->pid[a].p + own_begin);
   LAUNCH(c, k_permute_fluid, cdiv(n_src, 128), 128, c->dSt.p, c->sorted_src_f.p, pos + own_begin, vel + own_begin, c->kappa[a].p + own_begin,
          c->kappav[a].p + own_begin, c->pid[a].p + own_begin, c->pstate[a].p + own_begin, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p,
          c->kappav[b].p, c->pid[b].p, c->pstate[b].p);
@@ -998,12 +999,12 @@ int launch_step(dfr_context *c) {
   }
   if (c->P.n_bodies > 0) {
     if (c->slab.on) {  // per-body force / torque / Jacobian rows: sum over the slabs, then every rank advances the bodies alike
-      LAUNCH(c, k_body_rows_to_buf, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p, c->slab.body_buf.p);
+      LAUNCH(c, k_body_rows_to_buf, c->P.n_bodies, 256, c->dBodies.p, c->acc_rows.p, c->slab.body_buf.p);
       rc = slab_allreduce(c, c->slab.body_buf.p, (size_t)c->P.n_bodies * ACC_N, ncclDouble, ncclSum);
       if (rc) return rc;
       LAUNCH(c, k_body_buf_apply, c->P.n_bodies, 32, c->dBodies.p, c->slab.body_buf.p);
     } else
-      LAUNCH(c, k_body_reduce, c->P.n_bodies, 96, c->dBodies.p, c->acc_rows.p);
+      LAUNCH(c, k_body_reduce, c->P.n_bodies, 256, c->dBodies.p, c->acc_rows.p);
     if (c->cfg.use_rigid_contact_solver) {
       LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_PRE);
       if (c->n_dyn_p > 0) {

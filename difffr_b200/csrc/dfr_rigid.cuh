@@ -58,20 +58,37 @@ __global__ void k_reset_gradient(const __grid_constant__ Params P, BodyDev *bodi
 // sums the accumulator rows of each body in block order (deterministic) and clears them
 // (replaces accumulate_and_reset_gradient, BoundaryModel_Akinci2012.cpp:453-497, and the per-thread
 // force slots of BoundaryModel.cpp:38-54)
+#define BR_SLICES 8
+// Sum (and clear) the accumulator rows of one body into tot[ACC_N] (shared memory), whole block.  Rows are dealt to
+// BR_SLICES slices (row r -> slice r % BR_SLICES), each summed in row order, slices added in order: a fixed shape, so
+// the sums are reproducible, with BR_SLICES independent chains per column instead of one serial walk over all rows.
+__device__ __forceinline__ void body_rows_sum(const BodyDev &B, double *acc_rows, double (*part)[ACC_N], double *tot) {
+  for (int t = threadIdx.x; t < ACC_N * BR_SLICES; t += blockDim.x) {
+    const int k = t % ACC_N, sl = t / ACC_N;
+    double s = 0.0;
+    if (B.dynamic)
+      for (int r = sl; r < B.blk_count; r += BR_SLICES) {
+        double *p = acc_rows + (size_t)(B.blk_begin + r) * ACC_N + k;
+        s += *p;
+        *p = 0.0;
+      }
+    part[sl][k] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < ACC_N; k += blockDim.x) {
+    double s = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < BR_SLICES; sl++) s += part[sl][k];
+    tot[k] = s;
+  }
+  __syncthreads();
+}
 __global__ void k_body_reduce(BodyDev *bodies, double *acc_rows) {
   BodyDev &B = bodies[blockIdx.x];
   if (!B.dynamic) return;
   __shared__ double tot[ACC_N];
-  for (int k = threadIdx.x; k < ACC_N; k += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < B.blk_count; r++) {
-      double *p = acc_rows + (size_t)(B.blk_begin + r) * ACC_N + k;
-      s += *p;
-      *p = 0.0;
-    }
-    tot[k] = s;
-  }
-  __syncthreads();
+  __shared__ double part[BR_SLICES][ACC_N];
+  body_rows_sum(B, acc_rows, part, tot);
   if (threadIdx.x == 0) {
     B.force += mk3(tot[ACC_F], tot[ACC_F + 1], tot[ACC_F + 2]);
     B.torque += mk3(tot[ACC_T], tot[ACC_T + 1], tot[ACC_T + 2]);

@@ -81,9 +81,12 @@ __global__ void k_slab_set_nf(StepState *st, int nf) {
 
 // cells are sorted by source slot (k_bin_sort_cells); here by particle id, so that two ranks holding the same particles
 // in a cell order them identically
-__global__ void k_bin_sort_cells_by_id(const unsigned int *cell_start, int ncells, int *sorted_src, const int *pid_src) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
+// (driven from the particles like k_bin_sort_cells_by_particle: the particle that drew rank 0 sorts its cell)
+__global__ void k_bin_sort_cells_by_id(int n, const unsigned int *cell_start, const int *cell_of_particle, const int *rank_in_cell,
+                                       int *sorted_src, const int *pid_src) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || rank_in_cell[t] != 0) return;
+  const int c = cell_of_particle[t];
   const int s = (int)cell_start[c], e = (int)cell_start[c + 1];
   int *a = sorted_src + s;
   for (int i = 1; i < e - s; i++) {  // insertion sort: cells hold a handful of particles
@@ -174,16 +177,10 @@ __global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned lo
 // k_body_reduce split in two around the all-reduce of the per-body rows
 __global__ void k_body_rows_to_buf(const BodyDev *bodies, double *acc_rows, double *buf) {
   const BodyDev &B = bodies[blockIdx.x];
-  for (int k = threadIdx.x; k < ACC_N; k += blockDim.x) {
-    double s = 0.0;
-    if (B.dynamic)
-      for (int r = 0; r < B.blk_count; r++) {
-        double *p = acc_rows + (size_t)(B.blk_begin + r) * ACC_N + k;
-        s += *p;
-        *p = 0.0;
-      }
-    buf[(size_t)blockIdx.x * ACC_N + k] = s;
-  }
+  __shared__ double tot[ACC_N];
+  __shared__ double part[BR_SLICES][ACC_N];
+  body_rows_sum(B, acc_rows, part, tot);
+  for (int k = threadIdx.x; k < ACC_N; k += blockDim.x) buf[(size_t)blockIdx.x * ACC_N + k] = tot[k];
 }
 __global__ void k_body_buf_apply(BodyDev *bodies, const double *buf) {
   BodyDev &B = bodies[blockIdx.x];
