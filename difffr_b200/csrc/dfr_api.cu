@@ -159,6 +159,7 @@ struct dfr_context {
 
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
+  int div_pred_streak = 2;  // consecutive steps whose divergence-iteration count matched the speculated one
   double device_ms = 0.0;
   int64_t launches = 0;
   int launch_nf = 0;
@@ -852,8 +853,12 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
   if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at);
   if (PRESSURE)
     c->spec_prs = std::max(used, c->cfg.min_iterations);
-  else
+  else {
+    // the fused non-pressure pass only pays when the iteration count is predictable: count how long the speculated
+    // count (= the previous step's) has been right
+    c->div_pred_streak = (used == c->spec_div) ? std::min(c->div_pred_streak + 1, 1000) : 0;
     c->spec_div = std::max(used, 1);
+  }
 #undef RHO_ARGS
 #undef PUSH_ARGS
   return DFR_OK;
@@ -951,7 +956,7 @@ int launch_step(dfr_context *c) {
   const int no_fusion = getenv_int("DFR_NO_FUSION");
   const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && no_fusion != 1;
   const bool fuse_normals = fuse && c->cfg.surface_tension_method == 2;
-  const bool fuse_nonpressure = fuse && no_fusion != 2;
+  const bool fuse_nonpressure = fuse && no_fusion != 2 && c->div_pred_streak >= 2;
   if (!fuse) {
     PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
            c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
@@ -1121,6 +1126,7 @@ int reset_device_state(dfr_context *c) {
   }
   CU(cudaStreamSynchronize(c->stream));
   c->spec_div = 1;
+  c->div_pred_streak = 2;
   c->spec_prs = std::max(2, c->cfg.min_iterations);
   c->device_ms = 0.0;
   c->launches = 0;
