@@ -850,7 +850,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
     spec = 1;
   }
   const int used = PRESSURE ? c->hSt->prs_iters : c->hSt->div_iters;
-  if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at);
+  if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at && getenv_int("DFR_NO_FUSION") != 3);
   if (PRESSURE)
     c->spec_prs = std::max(used, c->cfg.min_iterations);
   else {
@@ -952,7 +952,8 @@ int launch_step(dfr_context *c) {
   g = cdiv(n, 128);
   int a = c->cur;
   // with the divergence solve and its warm start on, density/factor, the normals and the non-pressure accelerations ride
-  // on k_rho passes of that solve (dfr_kernels.cuh: RhoExtra); DFR_NO_FUSION=1 switches all of it off, =2 only the last
+  // on k_rho passes of that solve (dfr_kernels.cuh: RhoExtra); DFR_NO_FUSION=1 switches all of it off, =2 only the last,
+  // =3 (tests) runs the fused non-pressure pass but always discards it in favour of k_nonpressure
   const int no_fusion = getenv_int("DFR_NO_FUSION");
   const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && no_fusion != 1;
   const bool fuse_normals = fuse && c->cfg.surface_tension_method == 2;

@@ -92,6 +92,28 @@ def test_per_step_state_and_sensitivities(gpu_factory, oracle_factory, gradient_
     assert worst <= 1e-9  # observed ~1e-13: only summation order differs
 
 
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
+def test_pass_fusion_modes_agree(gpu_factory, oracle_factory, mode, monkeypatch):
+    """density/factor, normals and the non-pressure forces ride on k_rho passes of the divergence solve by default
+    (DESIGN.md §4).  DFR_NO_FUSION=1 runs every pass as its own kernel, =2 only the non-pressure pass, =3 runs the
+    fused non-pressure pass and then discards it (the path taken when the solve needs more iterations than
+    speculated): all of them must match the oracle and the default path."""
+    sc = scenes.dam_break_scene(4000, n_boxes=1)
+    ref = scenes.build_context(gpu_factory, sc, **BASE_CFG)
+    ref.step(6)
+    monkeypatch.setenv("DFR_NO_FUSION", mode)  # read by dfr_step at every step
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc)
+    for _ in range(6):
+        gpu.step(1)
+        orc.step(1)
+        compare_step(gpu, orc, sc)
+    for f in FLUID_FIELDS:
+        assert rel_err(gpu.fluid(f), ref.fluid(f)) <= 1e-11, f
+    sg, sr = gpu.body_state(1), ref.body_state(1)
+    for k in sg:
+        assert rel_err(sg[k], sr[k]) <= 1e-11, k
+
+
 @pytest.mark.parametrize("cfg", [
     dict(rigid_body_mode=1),
     dict(optimize_rotation=0),
