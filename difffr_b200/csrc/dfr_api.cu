@@ -830,6 +830,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
         fused_at = spec;
       } else
         PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
+      LAUNCH(c, k_residual_finish<PRESSURE>, 1, RES_THREADS, c->P, c->dSt.p, c->partials.p);
       if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
@@ -1142,6 +1143,24 @@ static void put(double *out, const Mat<R, C> &m) {
 }
 
 // ===============================================================================================
+// Shared-memory carve-out hint for the gather kernels that own static shared memory (residual / CFL reductions): they
+// live off the L1, but too small a carve-out limits their residency.  DFR_CARVEOUT_PCT (tuning): percent of the
+// unified L1/shared array asked for, -1 = leave the driver's default.
+template <class K>
+void carveout_hint(K kernel, int pct) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+void set_cache_preferences() {
+  const char *v = std::getenv("DFR_CARVEOUT_PCT");
+  const int pct = (v && *v) ? std::atoi(v) : -1;
+  if (pct < 0) return;
+  carveout_hint(k_rho<false, RHO_ITER, RHO_X_NONE>, pct);
+  carveout_hint(k_rho<true, RHO_ITER, RHO_X_NONE>, pct);
+  carveout_hint(k_rho<false, RHO_ITER, RHO_X_NONPRESSURE>, pct);
+  carveout_hint(k_nonpressure, pct);
+  cudaGetLastError();  // the hint is best effort
+}
+
 extern "C" {
 
 void dfr_default_config(dfr_config *cfg) {
@@ -1369,6 +1388,7 @@ int dfr_finalize(dfr_context *c) {
   if (!c) return DFR_ERR_INVALID;
   if (c->finalized) return fail(c, DFR_ERR_STATE, "already finalized");
   cudaSetDevice(c->device);
+  set_cache_preferences();
   const dfr_config &cfg = c->cfg;
   Params &P = c->P;
   std::memset(&P, 0, sizeof(P));
@@ -1565,7 +1585,7 @@ int dfr_finalize(dfr_context *c) {
     CU(c->pid[k].alloc(N)); CU(c->pstate[k].alloc(N));
   }
   CU(c->acc.alloc(N)); CU(c->sgp.alloc(N)); CU(c->normal.alloc(N)); CU(c->density.alloc(N)); CU(c->factor.alloc(N));
-  CU(c->dadv.alloc(N)); CU(c->xk.alloc(N)); CU(c->xrho.alloc(N)); CU(c->partials.alloc(N / 128 + 2));
+  CU(c->dadv.alloc(N)); CU(c->xk.alloc(N)); CU(c->xrho.alloc(N)); CU(c->partials.alloc((N / 128 + 2) * 4));
   CU(c->pos_init.alloc(N)); CU(c->vel_init.alloc(N)); CU(c->kappa_init.alloc(N)); CU(c->kappav_init.alloc(N));
   const size_t NB = (size_t)std::max(c->n_b, 1);
   CU(c->bpos.alloc(NB)); CU(c->bvel.alloc(NB)); CU(c->bx0.alloc(NB)); CU(c->bbody.alloc(NB)); CU(c->borig.alloc(NB));

@@ -940,66 +940,64 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
     }
   }
   if (MODE == RHO_ITER) {
-    // deterministic residual: block partials in a fixed order, last block closes the iteration
-    __shared__ double wsum[4];
-    __shared__ bool is_last;
+    // deterministic residual: one partial per warp, summed in a fixed order by k_residual_finish (no shared memory,
+    // barrier, fence or ticket here: they cost every iteration pass ~20 us against the plain passes)
     double s = err;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(DFR_FULL, s, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      partials[vb_] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
-      __threadfence();
-      const unsigned int nblk = (unsigned int)((nf + 127) / 128);
-      const unsigned int t = atomicAdd(&st->ticket, 1u);
-      is_last = (t == nblk - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      const int nblk = (nf + 127) / 128;
-      // fixed assignment of partials to threads, eight independent chains so that the L2 reads overlap (this block
-      // runs alone after all others: a serial chain of ~64 dependent reads cost ~20 us per iteration launch)
-      double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      int b = threadIdx.x;
-      for (; b + 7 * 128 < nblk; b += 8 * 128) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) a8[u] += __ldcg(partials + b + u * 128);
-      }
-      for (; b < nblk; b += 128) a8[0] += __ldcg(partials + b);
-      const double acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-      // fixed-shape tree over the 128 strided sums
-      __shared__ double red[128];
-      red[threadIdx.x] = acc;
-      __syncthreads();
-      for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0 && P.slab) {  // the stopping rule needs the sum over all slabs: k_solver_decide applies it
-        st->res_sum = red[0];
-        st->ticket = 0;
-      } else if (threadIdx.x == 0) {
-        const double avg = red[0] / (double)nf;
-        st->last_residual = avg;
-        st->ticket = 0;
-        if (PRESSURE) {
-          const double eta = P.max_error * 0.01 * P.density0;
-          const int it = st->prs_iters + 1;
-          st->prs_iters = it;
-          const bool chk = (avg <= eta);
-          if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
-        } else {
-          const double eta = (1.0 / h) * P.max_error_v * 0.01 * P.density0;
-          const int it = st->div_iters + 1;
-          st->div_iters = it;
-          const bool chk = (avg <= eta);
-          if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
-        }
-      }
-    }
+    if ((threadIdx.x & 31) == 0) partials[(size_t)vb_ * 4 + (threadIdx.x >> 5)] = s;
   }
+  }
+}
+
+// Closes a Jacobi iteration: sums the per-warp residual partials of k_rho<..., RHO_ITER> in a fixed order and applies
+// the stopping rules of pressureSolve / divergenceSolve (TimeStepDiffDFSPH.cpp:711-743, :828-861); one block.
+// Slab-decomposed contexts only store the local sum: the rule needs the sum over all slabs (k_solver_decide).
+#define RES_THREADS 1024
+template <bool PRESSURE>
+__global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_constant__ Params P, StepState *st, const double *partials) {
+  if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+  const int nf = st->nf;
+  const int np = ((nf + 127) / 128) * 4;
+  // fixed assignment of partials to threads; eight independent chains per thread so that the reads overlap
+  double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int b = threadIdx.x;
+  for (; b + 7 * RES_THREADS < np; b += 8 * RES_THREADS) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) a8[u] += partials[b + u * RES_THREADS];
+  }
+  for (; b < np; b += RES_THREADS) a8[0] += partials[b];
+  double v = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+  // fixed-shape tree: xor butterfly inside the warp, then over the 32 warp sums
+  __shared__ double wsum[RES_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DFR_FULL, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  v = wsum[threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DFR_FULL, v, o);
+  if (threadIdx.x != 0) return;
+  double red[1] = {v};
+  if (P.slab) {
+    st->res_sum = red[0];
+    return;
+  }
+  const double avg = red[0] / (double)nf;
+  st->last_residual = avg;
+  if (PRESSURE) {
+    const double eta = P.max_error * 0.01 * P.density0;
+    const int it = st->prs_iters + 1;
+    st->prs_iters = it;
+    const bool chk = (avg <= eta);
+    if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
+  } else {
+    const double eta = (1.0 / st->h_step) * P.max_error_v * 0.01 * P.density0;
+    const int it = st->div_iters + 1;
+    st->div_iters = it;
+    const bool chk = (avg <= eta);
+    if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
   }
 }
 
