@@ -20,4 +20,4 @@ if not _os.path.exists(_lib):
 _ctypes.CDLL(_lib, mode=_ctypes.RTLD_GLOBAL)  # _core links against it by soname
 
 from ._core import *  # noqa: E402,F401,F403
-from ._core import Exec, GUI, Utilities, DfrError, _load_scene_summary, _read_bgeo, _write_bgeo, _bgeo_of_state_file  # noqa: E402,F401
+from ._core import Exec, GUI, Utilities, DfrError, _load_scene_summary, _load_scene_full, _read_bgeo, _write_bgeo, _bgeo_of_state_file  # noqa: E402,F401

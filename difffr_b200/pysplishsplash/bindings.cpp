@@ -319,4 +319,36 @@ PYBIND11_MODULE(_core, m) {
     d["num_emitters"] = sc.emitters.size();
     return d;
   }, "scene_file"_a, "param"_a = "");
+  // the complete scene as the loader hands it to the C ABI: dfr_config as raw bytes (difffr_b200.cabi.Config), fluid
+  // particles, and per body the scaled body-frame samples with pose and initial velocities.  Used by
+  // tests/golden/make_paper_golden.py to drive the reference build and the CUDA path with identical inputs.
+  m.def("_load_scene_full", [](const std::string &file, const std::string &param) {
+    Scene sc = load_scene(file, param);
+    py::dict d;
+    d["config"] = py::bytes(reinterpret_cast<const char *>(&sc.cfg), sizeof(sc.cfg));
+    auto arr = [](const std::vector<double> &v) {
+      py::array_t<double> a({(py::ssize_t)(v.size() / 3), (py::ssize_t)3});
+      if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(double));
+      return a;
+    };
+    d["fluid_x"] = arr(sc.fluid_x);
+    d["fluid_v"] = arr(sc.fluid_v);
+    py::list bodies;
+    for (const BodyDesc &b : sc.bodies) {
+      py::dict bd;
+      bd["samples"] = arr(b.samples);
+      bd["dynamic"] = b.dynamic;
+      bd["density"] = b.density;
+      bd["translation"] = np_vec3(b.translation);
+      py::array_t<double> q(4);
+      for (int k = 0; k < 4; k++) q.mutable_data()[k] = b.rotation[k];
+      bd["rotation"] = q;
+      bd["init_v"] = np_vec3(b.init_v);
+      bd["init_omega"] = np_vec3(b.init_omega);
+      bodies.append(bd);
+    }
+    d["bodies"] = bodies;
+    d["num_emitters"] = sc.emitters.size();
+    return d;
+  }, "scene_file"_a, "param"_a = "");
 }

@@ -1,0 +1,143 @@
+"""Golden vectors of a PAPER scene, recorded from the REFERENCE's own code (oracle/_ref/libref.so).
+
+BASELINE.json configs[2] "bottle flipping stage 2": experiments/rigid_body_trajectory_optimization/scene/
+diff-bottle-model-collide.json + state/bottle_flip/state_54_particle_Fluid.bgeo (13,312 fluid particles inside a
+dynamic bottle of 13,085 boundary samples, penalty rigid-rigid contact solver + gradient manager, 0.25 s velocity ramp).
+The scene is parsed and its meshes sampled by this repository's host loader (difffr_b200/host/scene_host.hpp, the
+same code the pysplishsplash mirror runs), the resulting arrays drive the reference build, and inputs + outputs go into
+tests/golden/paper_bottle_stage2.npz so that the tests need neither /root/reference nor oracle/_ref:
+  python tests/golden/make_paper_golden.py            (build container only)
+Two segments of 24 steps from the same inputs: "paper" is the scene as shipped (the body is `animated` during the 0.25 s
+velocity ramp and carries no Jacobians); "short_ramp" only lowers uniformAccelerateRBTime to 0.004 s so that the free
+bottle, with fluid forces, Jacobians, manager blocks and sensitivities, falls inside the window (12 ramp + 12 free steps,
+up to 46 pressure / 36 divergence iterations per step).  The window is short on purpose.  This scene amplifies rounding
+differences between any two FP-different implementations (the reference with another thread count included): the
+manager's omega-sensitivity recurrence grows them ~3x per step during the ramp (1e-18 -> 1e-3 in 40 steps), the free
+bottle's state goes from 5e-11 to 1e-5 within 15 steps (net force = small difference of large pressure forces), and
+after ~45 steps one borderline convergence decision (15 vs 14 pressure iterations) separates the trajectories for good.
+Recorded per step: rigid state, force/torque, iteration counts, time step, all 16 sensitivity blocks and the manager
+blocks; the fluid
+fields (every 4th particle) after step 8.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+REF = "/root/reference/experiments/rigid_body_trajectory_optimization"
+SCENE = os.path.join(REF, "scene", "diff-bottle-model-collide.json")
+STATE = os.path.join(REF, "state", "bottle_flip", "state_54_particle_Fluid.bgeo")
+FLUID_FIELDS = ["position", "velocity", "kappa", "density_adv"]  # of every 4th particle (fixture size)
+STEPS = int(os.environ.get("PAPER_GOLDEN_STEPS", "24"))
+FLUID_STEP = 8  # fluid fields are recorded after this step (later the sloshing fluid has amplified rounding differences too far)
+# segment name -> overrides of the scene's configuration
+SEGMENTS = {
+    "paper": {},                                   # the scene as shipped: 0.25 s velocity ramp (the body is `animated`)
+    "short_ramp": {"uniform_acc_rb_time": 0.004},  # same scene and state, ramp over after ~5 steps: fluid forces, Jacobians,
+}                                                  # manager blocks and sensitivities of the free bottle within the window
+
+
+def run_segment(seg):
+    from pysph_util import import_sph
+    from difffr_b200.cabi import Config, Context
+
+    sph = import_sph()
+    sc = sph._load_scene_full(SCENE, "")
+    st = sph._read_bgeo(STATE)
+    cfg = Config.from_buffer_copy(sc["config"])
+    for k, v in SEGMENTS[seg].items():
+        setattr(cfg, k, v)
+    assert st["n"] == sc["fluid_x"].shape[0] == 13312
+    rlib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    ctx = Context(config=cfg, lib=rlib, prefix="ref_")
+    ctx.set_fluid(sc["fluid_x"], sc["fluid_v"])
+    for b in sc["bodies"]:
+        ctx.add_body(b["samples"], bool(b["dynamic"]), float(b["density"]), b["translation"], b["rotation"])
+    for i, b in enumerate(sc["bodies"]):
+        if b["dynamic"]:
+            ctx.set_init_v_omega(i, b["init_v"], b["init_omega"])
+    ctx.finalize()
+    ctx.load_fluid_state(st["x"], st["v"], st["kappa"], st["kappa_v"])
+    out = {}
+    if seg == "paper":  # the inputs, stored once
+        out.update({"config_bytes": np.frombuffer(sc["config"], dtype=np.uint8), "fluid_x": sc["fluid_x"], "fluid_v": sc["fluid_v"],
+                    "n_bodies": len(sc["bodies"]), "steps": STEPS, "fluid_step": FLUID_STEP, "segments": np.array(list(SEGMENTS.keys())),
+                    "state_x": st["x"], "state_v": st["v"], "state_kappa": st["kappa"], "state_kappa_v": st["kappa_v"]})
+        for i, b in enumerate(sc["bodies"]):
+            out[f"body{i}_samples"] = b["samples"]
+            out[f"body{i}_dynamic"] = int(b["dynamic"])
+            out[f"body{i}_density"] = float(b["density"])
+            out[f"body{i}_translation"] = b["translation"]
+            out[f"body{i}_rotation"] = b["rotation"]
+            out[f"body{i}_init_v"] = b["init_v"]
+            out[f"body{i}_init_omega"] = b["init_omega"]
+            out[f"body{i}_volume_sum"] = float(np.sum(ctx.body_particles(i, "volume")))
+    dyn = [i for i, b in enumerate(sc["bodies"]) if b["dynamic"]]
+    b = dyn[0]
+    if seg == "paper":
+        out[f"body{b}_volume"] = ctx.body_particles(b, "volume")
+    P = seg + "_"
+    out[P + "cfg_keys"] = np.array(list(SEGMENTS[seg].keys()))
+    out[P + "cfg_vals"] = np.array([float(v) for v in SEGMENTS[seg].values()])
+    rec = {k: [] for k in ("time", "h", "iters", "iters_v", "finished")}
+    states, fts, grads, mgrs = [], [], [], []
+    for s in range(STEPS):
+        ctx.step(1)
+        info = ctx.step_info()
+        rec["time"].append(info.time)
+        rec["h"].append(info.time_step_size)
+        rec["iters"].append(info.iterations)
+        rec["iters_v"].append(info.iterations_v)
+        rec["finished"].append(info.trajectory_finished)
+        bs = ctx.body_state(b)
+        states.append(np.concatenate([bs["x"], bs["q"], bs["v"], bs["omega"]]))
+        pr = ctx.body_properties(b)
+        fts.append(np.concatenate([pr["force"], pr["torque"]]))
+        g = np.zeros((16, 12))
+        m = np.zeros((16, 12))
+        for w in range(16):
+            a = ctx.body_grad(b, w).ravel()
+            g[w, : a.size] = a
+            a = ctx.manager_grad(b, b, w).ravel()
+            m[w, : a.size] = a
+        grads.append(g)
+        mgrs.append(m)
+        if s + 1 == FLUID_STEP:
+            for f in FLUID_FIELDS:
+                out[P + "fluid_" + f] = ctx.fluid(f)[::4]
+        print(seg, "step", s + 1, "t", info.time, "h", info.time_step_size, "it", info.iterations, info.iterations_v, flush=True)
+    for k, v in rec.items():
+        out[P + "step_" + k] = np.array(v)
+    out[P + "body_state"] = np.array(states)
+    out[P + "body_force_torque"] = np.array(fts)
+    out[P + "body_grads"] = np.array(grads)
+    out[P + "manager_grads"] = np.array(mgrs)
+    np.savez_compressed(os.path.join(HERE, f"_paper_seg_{seg}.npz"), **out)
+
+
+def main():
+    import subprocess
+
+    if len(sys.argv) > 1:  # one reference context per process (the reference keeps its state in singletons)
+        run_segment(sys.argv[1])
+        return
+    merged = {}
+    for seg in SEGMENTS:
+        subprocess.run([sys.executable, os.path.abspath(__file__), seg], check=True)
+        part = os.path.join(HERE, f"_paper_seg_{seg}.npz")
+        with np.load(part) as z:
+            merged.update({k: z[k] for k in z.files})
+        os.remove(part)
+    path = os.path.join(HERE, "paper_bottle_stage2.npz")
+    np.savez_compressed(path, **merged)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
