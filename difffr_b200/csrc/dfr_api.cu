@@ -159,6 +159,7 @@ struct dfr_context {
 
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
+  int fresh_steps = 4;      // steps since finalize / reset / load during which the list capacities are checked eagerly
   int div_pred_streak = 2;  // consecutive steps whose divergence-iteration count matched the speculated one
   double device_ms = 0.0;
   int64_t launches = 0;
@@ -937,6 +938,52 @@ int contact_rest_state(dfr_context *c) {
 }
 
 // one SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169)
+// Neighbour rows that do not fit their ELL capacity: the reference has no such limit (vector<vector<unsigned>>), so the
+// capacities grow and the lists are rebuilt - the sort is done and nothing else of the step has run yet.  The check
+// needs a host read-back right after the list build, so it is only made while rows may plausibly overflow: in the
+// first steps after finalize / reset / load, and whenever the longest row of the previous step was above half the
+// capacity (a row does not double within one step of a CFL-limited simulation).  Otherwise an overflow still surfaces
+// as DFR_ERR_CAPACITY at the step's first read-back.  Slab-decomposed contexts keep the fixed capacities.
+int ensure_list_capacity(dfr_context *c) {
+  if (c->slab.on) return DFR_OK;
+  const bool risky = c->fresh_steps > 0 || 2 * (int)c->hSt->list_used_f > c->cap_f || 2 * (int)c->hSt->list_used_b > c->cap_b ||
+                     2ull * c->hSt->list_used_d > c->cap_d;
+  if (c->fresh_steps > 0) c->fresh_steps--;
+  if (!risky) return DFR_OK;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int flags = c->hSt->error_flags & 7;
+    if (!flags) return DFR_OK;
+    const size_t nwarp = ((size_t)c->nf_cap + 31) / 32;
+    if (flags & 1) {
+      const int want = (std::max(2 * c->cap_f, (int)(c->hSt->list_used_f * 5 / 4) + 8) + 3) & ~3;
+      if (want > 4096) break;
+      c->idx_f.free();
+      CU(c->idx_f.alloc(nwarp * 32 * (size_t)want));
+      c->cap_f = want;
+    }
+    if (flags & 2) {
+      const int want = (std::max(2 * c->cap_b, (int)(c->hSt->list_used_b * 5 / 4) + 8) + 3) & ~3;
+      if (want > 4096) break;
+      c->idx_b.free();
+      CU(c->idx_b.alloc(nwarp * 32 * (size_t)want));
+      c->cap_b = want;
+    }
+    if (flags & 4) {
+      const unsigned long long want = std::max<unsigned long long>(2ull * c->cap_d, (unsigned long long)c->hSt->list_used_d * 5 / 4 + 1024);
+      if (want > (1ull << 31)) break;
+      c->idx_d.free();
+      CU(c->idx_d.alloc((size_t)want));
+      c->cap_d = (unsigned int)want;
+    }
+    CU(cudaMemsetAsync(&c->dSt.p->error_flags, 0, sizeof(int), c->stream));
+    int rc = build_neighbor_lists(c);
+    if (rc) return rc;
+  }
+  return sync_state(c);  // reports the capacity error
+}
+
 int launch_step(dfr_context *c) {
   int n = c->launch_nf, g = cdiv(n, 128);
   if (c->cfg.use_rigid_contact_solver) {  // TimeStepDiffDFSPH::performNeighborhoodSearch (:2044-2056): z-sort every 500 steps
@@ -948,6 +995,8 @@ int launch_step(dfr_context *c) {
   }
   LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p);
   int rc = build_neighbors(c);
+  if (rc) return rc;
+  rc = ensure_list_capacity(c);
   if (rc) return rc;
   n = c->launch_nf;  // slab mode: the number of local particles changes with every exchange
   g = cdiv(n, 128);
@@ -1128,6 +1177,7 @@ int reset_device_state(dfr_context *c) {
   }
   CU(cudaStreamSynchronize(c->stream));
   c->spec_div = 1;
+  c->fresh_steps = 4;
   c->div_pred_streak = 2;
   c->spec_prs = std::max(2, c->cfg.min_iterations);
   c->device_ms = 0.0;
@@ -2040,6 +2090,9 @@ int dfr_get_neighbors(dfr_context *c, int set_a, int set_b, int32_t *counts, int
   cudaSetDevice(c->device);
   // the same neighbourhood build the step runs, on the current positions
   int rc = build_neighbors(c);
+  if (rc) return rc;
+  c->fresh_steps = std::max(c->fresh_steps, 1);  // check the row capacities now
+  rc = ensure_list_capacity(c);
   if (rc) return rc;
   rc = sync_state(c);
   if (rc) return rc;

@@ -655,11 +655,11 @@ __global__ void __launch_bounds__(128) k_dnbr_fill(const __grid_constant__ Param
                                                     const unsigned int *off_d, int *idx_d, unsigned int cap_d) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_dyn) return;
+  if (t == 0 && lane == 0) st->list_used_d = off_d[n_dyn];
   if (off_d[t + 1] > cap_d) {
     if (lane == 0) atomicOr(&st->error_flags, 4);
     return;
   }
-  if (t == 0 && lane == 0) st->list_used_d = off_d[n_dyn];
   const double4 p = bpos[dyn_begin + t];
   int cx, cy, cz;
   cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);

@@ -16,6 +16,7 @@ __global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, Bo
     st->div_iters = 0;
     st->ticket = 0;
     st->cfl_max_bits = 0ull;
+    st->list_used_f = st->list_used_b = 0u;  // longest rows of THIS step's neighbour build (capacity watch, dfr_api.cu)
     if (!P.slab) {  // one context holds everything (emitters may have grown nf at the end of the last step)
       st->own_begin = 0;
       st->own_end = st->nf;

@@ -129,7 +129,8 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
             assert e <= state_tol, ("boundary volume sum", b, e)
         e = rel_err(ctx.body_particles(dyn[0], "volume"), g[f"body{dyn[0]}_volume"])
         assert e <= state_tol, ("boundary volume", e)
-        ctx.load_fluid_state(g["state_x"], g["state_v"], g["state_kappa"], g["state_kappa_v"])
+        if "state_x" in g.files:
+            ctx.load_fluid_state(g["state_x"], g["state_v"], g["state_kappa"], g["state_kappa_v"])
         b = dyn[0]
         for s in range(int(g["steps"])):
             ctx.step(1)
@@ -154,7 +155,7 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
             worst = max(worst, e)
             if s + 1 == int(g["fluid_step"]):
                 for f in ("position", "velocity", "kappa", "density_adv"):
-                    got, ref = ctx.fluid(f)[::4], g[P + "fluid_" + f]
+                    got, ref = ctx.fluid(f)[:: int(g["fluid_stride"])], g[P + "fluid_" + f]
                     # the shipped state file holds 22 particles with NaN positions; the reference carries them along
                     assert np.array_equal(np.isnan(got), np.isnan(ref)), (seg, f, "NaN pattern")
                     ok = ~np.isnan(ref)
@@ -166,9 +167,10 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
                 e = rel_err(a, g[P + "body_grads"][s, w, : a.size])
                 assert e <= grad_tol, (seg, s, GRAD_NAMES[w], e)
                 worst = max(worst, e)
-                a = ctx.manager_grad(b, b, w).ravel()
-                e = rel_err(a, g[P + "manager_grads"][s, w, : a.size])
-                assert e <= grad_tol, (seg, s, "manager", GRAD_NAMES[w], e)
-                worst = max(worst, e)
+                if P + "manager_grads" in g.files:
+                    a = ctx.manager_grad(b, b, w).ravel()
+                    e = rel_err(a, g[P + "manager_grads"][s, w, : a.size])
+                    assert e <= grad_tol, (seg, s, "manager", GRAD_NAMES[w], e)
+                    worst = max(worst, e)
         ctx.close()
     return worst

@@ -198,6 +198,19 @@ def test_reset_restores_the_initial_state_bit_exactly(gpu_factory):
         assert np.array_equal(ga[w], gpu.body_grad(1, w))
 
 
+def test_neighbour_capacities_grow_on_demand(gpu_factory, oracle_factory):
+    """The reference's neighbour lists have no capacity (vector<vector<unsigned>>).  The ELL rows here do; a row that
+    does not fit makes the context grow its capacities and rebuild the lists before anything else of the step has run."""
+    sc = scenes.dam_break_scene(4000, n_boxes=1)
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, neighbor_capacity_fluid=8, neighbor_capacity_boundary=4, body_neighbor_capacity=4)
+    compare_neighbors(gpu, orc, sc)
+    for _ in range(4):
+        gpu.step(1)
+        orc.step(1)
+        compare_step(gpu, orc, sc)
+    compare_neighbors(gpu, orc, sc)
+
+
 @pytest.mark.parametrize("case", ["fluid_only", "static_only", "sparse", "escaping"])
 def test_edge_cases(gpu_factory, oracle_factory, case):
     r = 0.025
