@@ -160,7 +160,6 @@ struct dfr_context {
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
   int fresh_steps = 4;      // steps since finalize / reset / load during which the list capacities are checked eagerly
-  int div_pred_streak = 2;  // consecutive steps whose divergence-iteration count matched the speculated one
   double device_ms = 0.0;
   int64_t launches = 0;
   int launch_nf = 0;
@@ -767,8 +766,9 @@ void launch_boundary_side(dfr_context *c, bool grad, int iter_kernel) {
 // solve, and the host looks at the flag only after the speculated batch.
 // fuse_density / fuse_normals (divergence solve with warm start only): the first two k_rho launches of the step also do
 // the work of k_density_factor and k_normals (dfr_kernels.cuh: RhoExtra)
-// fuse_nonpressure: the last launch of the first speculated batch of iterations also evaluates the non-pressure
-// accelerations; *nonpressure_done tells whether that launch really was the last active iteration.
+// fuse_nonpressure: the last launch of every speculated batch of iterations (the first batch holds as many iterations as
+// the previous step needed, every further batch one) also evaluates the non-pressure accelerations;
+// *nonpressure_done tells whether the last of those launches really was the last active iteration.
 template <bool PRESSURE>
 int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals = false, bool fuse_nonpressure = false,
                   bool *nonpressure_done = nullptr) {
@@ -815,6 +815,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
   int launched = 0;
   int spec = PRESSURE ? c->spec_prs : c->spec_div;
   int fused_at = -1;  // iteration count at which the fused non-pressure pass ran
+  const int first_batch = std::max(1, std::min(spec, max_it));
   for (;;) {
     spec = std::max(1, std::min(spec, max_it - launched));
     for (int it = 0; it < spec; it++) {
@@ -823,12 +824,12 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
       launch_boundary_side<PRESSURE>(c, true, 1);
       PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
       SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
-      if (!PRESSURE && fuse_nonpressure && launched == 0 && it == spec - 1) {
+      if (!PRESSURE && fuse_nonpressure && it == spec - 1) {  // the last launch of every batch may be the last iteration
         RhoExtra X = X0;
         X.normal = c->normal.p;
         X.acc = c->acc.p;
         PLAUNCH(c, (k_rho<false, RHO_ITER, RHO_X_NONPRESSURE>), g, RHO_ARGS_X(c->xrho.p, X));
-        fused_at = spec;
+        fused_at = launched + spec;
       } else
         PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
       LAUNCH(c, k_residual_finish<PRESSURE>, 1, RES_THREADS, c->P, c->dSt.p, c->partials.p);
@@ -849,18 +850,16 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
     if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
     const int active = PRESSURE ? c->hSt->prs_active : c->hSt->div_active;
     if (!active || launched >= max_it) break;
-    spec = 1;
+    // the prediction was too low: follow-up batches of 1, 2, 4, 8, 8, ... iterations (a read-back per batch; launches
+    // past convergence return at once)
+    spec = (launched <= first_batch) ? 1 : std::min(2 * spec, 8);
   }
   const int used = PRESSURE ? c->hSt->prs_iters : c->hSt->div_iters;
   if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at && getenv_int("DFR_NO_FUSION") != 3);
   if (PRESSURE)
     c->spec_prs = std::max(used, c->cfg.min_iterations);
-  else {
-    // the fused non-pressure pass only pays when the iteration count is predictable: count how long the speculated
-    // count (= the previous step's) has been right
-    c->div_pred_streak = (used == c->spec_div) ? std::min(c->div_pred_streak + 1, 1000) : 0;
+  else
     c->spec_div = std::max(used, 1);
-  }
 #undef RHO_ARGS
 #undef PUSH_ARGS
   return DFR_OK;
@@ -1007,7 +1006,7 @@ int launch_step(dfr_context *c) {
   const int no_fusion = getenv_int("DFR_NO_FUSION");
   const bool fuse = c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && no_fusion != 1;
   const bool fuse_normals = fuse && c->cfg.surface_tension_method == 2;
-  const bool fuse_nonpressure = fuse && no_fusion != 2 && c->div_pred_streak >= 2;
+  const bool fuse_nonpressure = fuse && no_fusion != 2;
   if (!fuse) {
     PLAUNCH(c, k_density_factor, g, c->P, c->dSt.p, c->pos[a].p, c->bpos.p, list_f(c), list_b(c), c->density.p, c->factor.p,
            c->sgp.p, c->xrho.p, ghost_out(c, GA_XRHO));
@@ -1178,7 +1177,6 @@ int reset_device_state(dfr_context *c) {
   CU(cudaStreamSynchronize(c->stream));
   c->spec_div = 1;
   c->fresh_steps = 4;
-  c->div_pred_streak = 2;
   c->spec_prs = std::max(2, c->cfg.min_iterations);
   c->device_ms = 0.0;
   c->launches = 0;
