@@ -322,9 +322,11 @@ def main():
     t0 = time.perf_counter()
     ctx.load_fluid_state(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())  # also resets the context
     d2h = 0
-    for _ in range(e2e_steps):
+    for k in range(e2e_steps):
         for b in dyn:
-            ctx.set_init_v_omega(b, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0))
+            # a control input that differs from the previous step's, so that the 48-byte H2D copy really happens every
+            # step (dfr_set_init_v_omega skips the copy for unchanged values); it only acts during the velocity ramp
+            ctx.set_init_v_omega(b, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0e-12 * (k & 1)))
         ctx.step(1)
         for b in dyn:
             ctx.body_state(b)
