@@ -1,6 +1,6 @@
-"""Size-independent properties at BASELINE.json's full size (1M fluid particles, 4 dynamic boxes), where the
-CPU oracle would take minutes: neighbour symmetry, run-to-run bit reproducibility, reset, conservation-style
-sanity (finite state, density near rest), and a coarse cross-check of the sensitivities by finite differences."""
+"""BASELINE.json's full size (the bench workload: 2^20 fluid particles, 4 dynamic boxes): two steps against the CPU oracle
+(about a second per step on the box's host cores), and size-independent properties where more steps are needed:
+neighbour symmetry, run-to-run bit reproducibility, reset, finite state and density near rest."""
 import numpy as np
 import pytest
 
@@ -13,6 +13,38 @@ CFG = dict(surface_tension_method=2, surface_tension=0.2, target_time=1.0, max_e
 @pytest.fixture(scope="module")
 def big_scene():
     return scenes.dam_break_scene(1 << 20, n_boxes=4)
+
+
+def test_two_steps_against_the_oracle_1m(gpu_factory, oracle_factory, big_scene):
+    """The bench workload itself, step by step against the oracle: iteration counts and time steps identical, fluid and
+    rigid state, forces and all 16 sensitivity blocks of the four boxes within the north-star tolerances (observed ~1e-12)."""
+    from conftest import rel_err
+
+    gpu = scenes.build_context(gpu_factory, big_scene, **CFG)
+    orc = scenes.build_context(oracle_factory, big_scene, **CFG)
+    worst = 0.0
+    for _ in range(2):
+        gpu.step(1)
+        orc.step(1)
+        ig, io = gpu.step_info(), orc.step_info()
+        assert (ig.iterations, ig.iterations_v) == (io.iterations, io.iterations_v)
+        assert abs(ig.time_step_size - io.time_step_size) <= 1e-12 * io.time_step_size
+        for f in ("position", "velocity", "density", "factor", "kappa", "kappa_v", "density_adv", "acceleration"):
+            e = rel_err(gpu.fluid(f), orc.fluid(f))
+            assert e <= 1e-6, (f, e)
+            worst = max(worst, e)
+        for body in range(1, 5):
+            sg, so = gpu.body_state(body), orc.body_state(body)
+            for k in sg:
+                e = rel_err(sg[k], so[k])
+                assert e <= 1e-6, (body, k, e)
+                worst = max(worst, e)
+            for w in range(16):
+                e = rel_err(gpu.body_grad(body, w), orc.body_grad(body, w))
+                assert e <= 1e-4, (body, w, e)
+                worst = max(worst, e)
+    assert worst <= 1e-8
+    orc.close()
 
 
 def test_neighbor_symmetry_and_counts_1m(gpu_factory, big_scene):
