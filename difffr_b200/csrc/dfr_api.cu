@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,7 @@ struct HostBody {
   int p_begin = 0;  // slice in the concatenated (unsorted) boundary layout
   int blk_begin = 0, blk_count = 0;  // accumulator rows of the boundary-side kernel
   BodyDev dev0;     // initial device record (reset() uploads it)
+  bool init_staged = false;  // dfr_set_init_v_omega values waiting in the pinned staging buffer
 };
 
 template <class T>
@@ -101,6 +103,8 @@ struct dfr_context {
   DevBuf<BodyDev> dBodies;
   BodyDev *h_bodies = nullptr;  // pinned mirror of dBodies, refreshed with the state read-back that ends every dfr_step
   bool bodies_mirrored = false;
+  double *h_init = nullptr;     // pinned staging of (init_v, init_omega) per body: uploaded at the start of the next step
+  bool init_dirty = false;
   bool slab_needs_p2p_setup = false;
   DevBuf<MgrBlock> dMgr;
   DevBuf<double> acc_rows;
@@ -1191,6 +1195,19 @@ static void put(double *out, const Mat<R, C> &m) {
 }
 
 // ===============================================================================================
+// (init_v, init_omega) values staged by dfr_set_init_v_omega -> device, in stream order
+int upload_staged_init(dfr_context *c) {
+  if (!c->init_dirty) return DFR_OK;
+  static_assert(offsetof(BodyDev, init_omega) == offsetof(BodyDev, init_v) + sizeof(d3), "init_v and init_omega are adjacent");
+  for (size_t b = 0; b < c->bodies.size(); b++) {
+    if (!c->bodies[b].init_staged) continue;
+    c->bodies[b].init_staged = false;
+    CU(cudaMemcpyAsync(&(c->dBodies.p + b)->init_v, c->h_init + 6 * b, 2 * sizeof(d3), cudaMemcpyHostToDevice, c->stream));
+  }
+  c->init_dirty = false;
+  return DFR_OK;
+}
+
 // Shared-memory carve-out hint for the gather kernels that own static shared memory (residual / CFL reductions): they
 // live off the L1, but too small a carve-out limits their residency.  DFR_CARVEOUT_PCT (tuning): percent of the
 // unified L1/shared array asked for, -1 = leave the driver's default.
@@ -1292,6 +1309,7 @@ void dfr_destroy(dfr_context *c) {
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->hSt) cudaFreeHost(c->hSt);
   if (c->h_bodies) cudaFreeHost(c->h_bodies);
+  if (c->h_init) cudaFreeHost(c->h_init);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1337,13 +1355,16 @@ int dfr_set_init_v_omega(dfr_context *c, int body, const double v0[3], const dou
   if (v0) std::memcpy(hb.init_v, v0, sizeof(hb.init_v));
   if (omega0) std::memcpy(hb.init_w, omega0, sizeof(hb.init_w));
   if (c->finalized && !same) {  // SimulationDataDiffDFSPH::get_init_v_rb is read at every beginStep
-    cudaSetDevice(c->device);
     hb.dev0.init_v = mk3(hb.init_v[0], hb.init_v[1], hb.init_v[2]);
     hb.dev0.init_omega = mk3(hb.init_w[0], hb.init_w[1], hb.init_w[2]);
-    BodyDev *d = c->dBodies.p + body;
-    CU(cudaMemcpyAsync(&d->init_v, &hb.dev0.init_v, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(&d->init_omega, &hb.dev0.init_omega, sizeof(d3), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    // staged in pinned memory and uploaded in stream order at the start of the next step / trajectory / reset: the
+    // control input of a step costs one asynchronous 48-byte copy, no synchronisation
+    for (int k = 0; k < 3; k++) {
+      c->h_init[6 * body + k] = hb.init_v[k];
+      c->h_init[6 * body + 3 + k] = hb.init_w[k];
+    }
+    hb.init_staged = true;
+    c->init_dirty = true;
   }
   return DFR_OK;
 }
@@ -1641,6 +1662,7 @@ int dfr_finalize(dfr_context *c) {
   CU(c->dBodies.alloc(std::max<size_t>(c->bodies.size(), 1)));
   CU(c->dMgr.alloc(std::max<size_t>(c->bodies.size() * c->bodies.size(), 1)));
   if (cudaMallocHost((void **)&c->h_bodies, std::max<size_t>(c->bodies.size(), 1) * sizeof(BodyDev)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
+  if (cudaMallocHost((void **)&c->h_init, std::max<size_t>(c->bodies.size(), 1) * 6 * sizeof(double)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
   const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
@@ -1809,6 +1831,10 @@ int dfr_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
   c->bodies_mirrored = false;
+  {
+    int rc = upload_staged_init(c);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; s++) {
     int rc = launch_step(c);
@@ -1832,6 +1858,10 @@ int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
   c->bodies_mirrored = false;
+  {
+    int rc = upload_staged_init(c);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(c->ev0, c->stream));
   int s = 0;
   while (s < max_steps) {
