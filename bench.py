@@ -239,6 +239,7 @@ def main():
                     help="sharding for --gpus > 1: one slab-decomposed scene (default) or independent rollouts")
     ap.add_argument("--particles", type=int, default=N_PARTICLES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-iteration-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -412,6 +413,34 @@ def main():
         except Exception:
             pass
 
+    # ---- wall time of one gradient iteration at a paper-scene size (BASELINE.json's third figure) ----
+    # the stone-skipping configuration's 237,699 fluid particles and ~1,450 steps, on the synthetic
+    # scene family: reset + one trajectory run to its end by dfr_run_trajectory (forward + sensitivities, one host
+    # read-back per step like the scripts' per-step callback) + the read of the final state and the eight blocks
+    gradient_iteration = None
+    if world == 1 and not args.no_iteration_leg:
+        n_it, steps_it = 237699, 1450
+        sc_it = make_scene(n_it)
+        cfg_it = dict(CFG)
+        cfg_it.update(cfl_method=0, time_step_size=1.0e-3, target_time=steps_it * 1.0e-3 - 0.5e-3)
+        ctx_it = scenes.build_context(lambda **k: Context(device=local_rank, **k), sc_it, **cfg_it)
+        ctx_it.run_trajectory(steps_it + 10)  # warm-up iteration (allocations, capacity checks)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx_it.reset()
+        done = ctx_it.run_trajectory(steps_it + 10)
+        for b in [i for i, bd in enumerate(sc_it["bodies"]) if bd["dynamic"]]:
+            ctx_it.body_state(b)
+            for w in range(8):
+                ctx_it.body_grad(b, w)
+        torch.cuda.synchronize()
+        dt_it = time.perf_counter() - t0
+        gradient_iteration = {"seconds": dt_it, "steps": int(done), "fluid_particles": ctx_it.num_fluid,
+                              "ms_per_step": 1e3 * dt_it / max(int(done), 1),
+                              "what": "dfr_reset + dfr_run_trajectory to the end of the trajectory + final state and sensitivity blocks; "
+                                      "synthetic dam break at the stone-skipping scene's size (237,699 particles, ~1,450 steps, fixed h = 1e-3)"}
+        ctx_it.close()
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
@@ -444,6 +473,7 @@ def main():
                   "nvlink_bytes_per_step_rank0": slab_info["exchanged_bytes"] / max(e2e_steps, 1)} if slab else None),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "gradient_iteration": gradient_iteration,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
