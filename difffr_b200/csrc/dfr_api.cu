@@ -836,7 +836,7 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
         fused_at = launched + spec;
       } else
         PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
-      LAUNCH(c, k_residual_finish<PRESSURE>, 1, RES_THREADS, c->P, c->dSt.p, c->partials.p);
+      LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS);
       if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
@@ -1654,7 +1654,7 @@ int dfr_finalize(dfr_context *c) {
     CU(c->pid[k].alloc(N)); CU(c->pstate[k].alloc(N));
   }
   CU(c->acc.alloc(N)); CU(c->sgp.alloc(N)); CU(c->normal.alloc(N)); CU(c->density.alloc(N)); CU(c->factor.alloc(N));
-  CU(c->dadv.alloc(N)); CU(c->xk.alloc(N)); CU(c->xrho.alloc(N)); CU(c->partials.alloc((N / 128 + 2) * 4));
+  CU(c->dadv.alloc(N)); CU(c->xk.alloc(N)); CU(c->xrho.alloc(N)); CU(c->partials.alloc((N / 128 + 2) * 4 + RES_BLOCKS));  // per-warp residual partials + the slice sums of k_residual_finish
   CU(c->pos_init.alloc(N)); CU(c->vel_init.alloc(N)); CU(c->kappa_init.alloc(N)); CU(c->kappav_init.alloc(N));
   const size_t NB = (size_t)std::max(c->n_b, 1);
   CU(c->bpos.alloc(NB)); CU(c->bvel.alloc(NB)); CU(c->bx0.alloc(NB)); CU(c->bbody.alloc(NB)); CU(c->borig.alloc(NB));

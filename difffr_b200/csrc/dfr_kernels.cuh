@@ -951,40 +951,55 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
 }
 
 // Closes a Jacobi iteration: sums the per-warp residual partials of k_rho<..., RHO_ITER> in a fixed order and applies
-// the stopping rules of pressureSolve / divergenceSolve (TimeStepDiffDFSPH.cpp:711-743, :828-861); one block.
+// the stopping rules of pressureSolve / divergenceSolve (TimeStepDiffDFSPH.cpp:711-743, :828-861).  RES_BLOCKS blocks
+// each sum one contiguous slice (fixed assignment, fixed tree), the block that finishes last adds the slice sums in
+// slice order and decides - the result does not depend on which block that is.
 // Slab-decomposed contexts only store the local sum: the rule needs the sum over all slabs (k_solver_decide).
-#define RES_THREADS 1024
+#define RES_THREADS 256
+#define RES_BLOCKS 16
 template <bool PRESSURE>
-__global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_constant__ Params P, StepState *st, const double *partials) {
+__global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_constant__ Params P, StepState *st, const double *partials,
+                                                                 double *slice_sums) {
   if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   const int nf = st->nf;
   const int np = ((nf + 127) / 128) * 4;
-  // fixed assignment of partials to threads; eight independent chains per thread so that the reads overlap
-  double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  int b = threadIdx.x;
-  for (; b + 7 * RES_THREADS < np; b += 8 * RES_THREADS) {
+  const int per = (np + RES_BLOCKS - 1) / RES_BLOCKS;
+  const int lo = blockIdx.x * per, hi = min(lo + per, np);
+  // fixed assignment of partials to threads; four independent chains per thread so that the reads overlap
+  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+  int b = lo + threadIdx.x;
+  for (; b + 3 * RES_THREADS < hi; b += 4 * RES_THREADS) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) a8[u] += partials[b + u * RES_THREADS];
+    for (int u = 0; u < 4; u++) a4[u] += partials[b + u * RES_THREADS];
   }
-  for (; b < np; b += RES_THREADS) a8[0] += partials[b];
-  double v = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-  // fixed-shape tree: xor butterfly inside the warp, then over the 32 warp sums
+  for (; b < hi; b += RES_THREADS) a4[0] += partials[b];
+  double v = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   __shared__ double wsum[RES_THREADS / 32];
+  __shared__ bool is_last;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DFR_FULL, v, o);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  v = wsum[threadIdx.x];
+  if (threadIdx.x == 0) {
+    double t = 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DFR_FULL, v, o);
-  if (threadIdx.x != 0) return;
-  double red[1] = {v};
+    for (int w = 0; w < RES_THREADS / 32; w++) t += wsum[w];
+    slice_sums[blockIdx.x] = t;
+    __threadfence();
+    is_last = (atomicAdd(&st->ticket, 1u) == RES_BLOCKS - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  st->ticket = 0;
+  double total = 0.0;
+#pragma unroll
+  for (int k = 0; k < RES_BLOCKS; k++) total += __ldcg(slice_sums + k);
   if (P.slab) {
-    st->res_sum = red[0];
+    st->res_sum = total;
     return;
   }
-  const double avg = red[0] / (double)nf;
+  const double avg = total / (double)nf;
   st->last_residual = avg;
   if (PRESSURE) {
     const double eta = P.max_error * 0.01 * P.density0;
