@@ -113,6 +113,7 @@ struct dfr_context {
 
   // grids
   DevBuf<unsigned int> cell_start_f, cell_start_s, cell_start_d, tile_sums;
+  DevBuf<unsigned char> near_s;  // per cell: a static boundary particle may be within reach (k_mark_near, marked once)
   DevBuf<int> cell_of_p, rank_in_cell, sorted_src_f, sorted_src_d, cell_of_b, rank_b;
   // neighbour lists
   DevBuf<int> cnt_f, cnt_b, idx_f, idx_b, idx_d;
@@ -427,7 +428,8 @@ int build_neighbor_lists(dfr_context *c) {
   int rc = build_dyn_grid(c);
   if (rc) return rc;
   PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
-         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b);
+         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
+         c->near_s.p);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
     LAUNCH(c, k_dnbr_count, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
@@ -1291,6 +1293,7 @@ void dfr_destroy(dfr_context *c) {
   c->bpos.free(); c->bvel.free(); c->bx0.free(); c->bpos_tmp.free(); c->bx0_tmp.free(); c->bbody.free(); c->borig.free();
   c->bbody_tmp.free(); c->borig_tmp.free(); c->bvol.free(); c->dBodies.free(); c->dMgr.free(); c->acc_rows.free();
   c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
+  c->near_s.free();
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
@@ -1664,6 +1667,8 @@ int dfr_finalize(dfr_context *c) {
   if (cudaMallocHost((void **)&c->h_bodies, std::max<size_t>(c->bodies.size(), 1) * sizeof(BodyDev)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   if (cudaMallocHost((void **)&c->h_init, std::max<size_t>(c->bodies.size(), 1) * 6 * sizeof(double)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
+  CU(c->near_s.alloc((size_t)nc));
+  CU(cudaMemsetAsync(c->near_s.p, 0, (size_t)nc, c->stream));
   const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
   CU(c->cell_of_p.alloc(N)); CU(c->rank_in_cell.alloc(N)); CU(c->sorted_src_f.alloc(N));
@@ -1744,6 +1749,7 @@ int dfr_finalize(dfr_context *c) {
     CU(cudaMemcpyAsync(c->bbody.p, c->bbody_tmp.p, ns * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->borig.p, c->borig_tmp.p, ns * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->h_borig.data(), c->borig.p, ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH(c, k_mark_near, cdiv(ns, 128), 128, c->P, c->bpos.p, ns, c->near_s.p);
     CU(cudaStreamSynchronize(c->stream));
     c->bpos_tmp.free(); c->bx0_tmp.free(); c->bbody_tmp.free(); c->borig_tmp.free();
   }

@@ -544,6 +544,23 @@ __global__ void k_permute_boundary(int n, const int *sorted_src, const double4 *
   orig_out[i] = orig_in[s];
 }
 
+// "A point of this set may be within reach": one byte per cell, set for every cell of the (2 reach + 1)^3 block around
+// the cell of each point - exactly the cells whose stencil walk (for_each_in_range) would visit that point's cell.
+// The list build reads the byte of a fluid particle's own cell and skips the whole 25-row walk over the static
+// boundary set when it is 0 (true for most of the fluid).  Marked once: static particles never move.  (Marking the
+// dynamic set every step as well was measured: it costs small scenes more than it saves.)
+__global__ void k_mark_near(const __grid_constant__ Params P, const double4 *pos, int n, unsigned char *near_flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double4 p = pos[t];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int R = P.grid.reach;
+  for (int z = max(cz - R, 0); z <= min(cz + R, P.grid.nz - 1); z++)
+    for (int y = max(cy - R, 0); y <= min(cy + R, P.grid.ny - 1); y++)
+      for (int x = max(cx - R, 0); x <= min(cx + R, P.grid.nx - 1); x++) near_flag[cell_lin(P.grid, x, y, z)] = 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // neighbour lists
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +596,8 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
 // host then grows the capacity and replays the step (dfr_api.cu: launch_step).
 __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
                                                     GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
-                                                    int *idx_f, int *idx_b, int cap_f, int cap_b, const VSched S) {
+                                                    int *idx_f, int *idx_b, int cap_f, int cap_b, const unsigned char *near_s,
+                                                    const VSched S) {
   vsched_prologue(S);
   const int n = st->nf;
   DFR_VB_LOOP(S) {
@@ -594,7 +612,10 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
       if (cf < cap_f) idx_f[nbr_slot(cap_f, i, cf)] = j;
       cf++;
     });
-    if (has_static) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int j) {
+    int ocx, ocy, ocz;
+    cell_of(P.grid, p.x, p.y, p.z, ocx, ocy, ocz);
+    const int own_cell = cell_lin(P.grid, ocx, ocy, ocz);
+    if (has_static && near_s[own_cell]) for_each_in_range(P, gs, p.x, p.y, p.z, -1, [&](int j) {
       if (cb < cap_b) idx_b[nbr_slot(cap_b, i, cb)] = j;
       cb++;
     });
