@@ -1095,7 +1095,9 @@ __global__ void __launch_bounds__(128, DFR_PUSH_BLOCKS) k_push(const __grid_cons
 // per-warp rows are combined in a fixed order (deterministic FP64 sums).
 // ---------------------------------------------------------------------------------------------
 #define BS_WARPS 4
-#define BS_PART_PER_BLOCK 8  // boundary particles per block (2 per warp): few dynamic particles, so many small blocks
+#ifndef BS_PART_PER_BLOCK
+#define BS_PART_PER_BLOCK 4  // boundary particles per block (1 per warp): few dynamic particles, so many small blocks
+#endif
 
 template <int MODE /*0 pressure, 1 divergence*/, bool GRAD>
 __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_constant__ Params P, const StepState *st, const BodyDev *bodies, const int *blk_body,

@@ -162,7 +162,7 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
                     e = rel_err(got[ok], ref[ok])
                     assert e <= state_tol, (seg, f, e)
                     worst = max(worst, e)
-            for w in range(16):
+            for w in range(16 if s < int(g["grad_steps"]) else 0):  # (make_paper_golden.py: where Jacobians are well conditioned)
                 a = ctx.body_grad(b, w).ravel()
                 e = rel_err(a, g[P + "body_grads"][s, w, : a.size])
                 assert e <= grad_tol, (seg, s, GRAD_NAMES[w], e)
