@@ -164,6 +164,7 @@ struct dfr_context {
 
   // bookkeeping
   int spec_div = 1, spec_prs = 2;
+  int div_pred_streak = 2;  // consecutive steps whose divergence-iteration count matched the speculated one
   int fresh_steps = 4;      // steps since finalize / reset / load during which the list capacities are checked eagerly
   double device_ms = 0.0;
   int64_t launches = 0;
@@ -830,7 +831,11 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
       launch_boundary_side<PRESSURE>(c, true, 1);
       PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
       SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
-      if (!PRESSURE && fuse_nonpressure && it == spec - 1) {  // the last launch of every batch may be the last iteration
+      // the last launch of a batch may be the last iteration: always in a follow-up batch (the solve did not converge in
+      // the predicted count, every further iteration probably is the last), in the first batch only while the
+      // prediction has been right lately - when the count alternates (1, 2, 1, 2, ...) a fused pass in the first batch is
+      // wasted or idle every time
+      if (!PRESSURE && fuse_nonpressure && it == spec - 1 && (launched > 0 || c->div_pred_streak >= 2)) {
         RhoExtra X = X0;
         X.normal = c->normal.p;
         X.acc = c->acc.p;
@@ -864,8 +869,10 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
   if (nonpressure_done) *nonpressure_done = (fused_at > 0 && used == fused_at && getenv_int("DFR_NO_FUSION") != 3);
   if (PRESSURE)
     c->spec_prs = std::max(used, c->cfg.min_iterations);
-  else
+  else {
+    c->div_pred_streak = (used == c->spec_div) ? std::min(c->div_pred_streak + 1, 1000) : 0;
     c->spec_div = std::max(used, 1);
+  }
 #undef RHO_ARGS
 #undef PUSH_ARGS
   return DFR_OK;
@@ -1182,6 +1189,7 @@ int reset_device_state(dfr_context *c) {
   }
   CU(cudaStreamSynchronize(c->stream));
   c->spec_div = 1;
+  c->div_pred_streak = 2;
   c->fresh_steps = 4;
   c->spec_prs = std::max(2, c->cfg.min_iterations);
   c->device_ms = 0.0;
