@@ -592,8 +592,8 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
 }
 
 // Single scan: fluid->fluid and fluid->boundary neighbour lists in a warp-interleaved ELL layout
-// (dfr_types.cuh: "ELL-4"; no count pass / prefix sum is needed).  Rows longer than cap raise error_flags; the
-// host then grows the capacity and replays the step (dfr_api.cu: launch_step).
+// (dfr_types.cuh: "ELL-4"; no count pass / prefix sum is needed).  Rows longer than cap raise error_flags and report
+// their length; the host then grows the capacity and rebuilds the lists (dfr_api.cu: ensure_list_capacity).
 __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
                                                     GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
                                                     int *idx_f, int *idx_b, int cap_f, int cap_b, const unsigned char *near_s,
