@@ -120,3 +120,24 @@ def test_reads_the_reference_bottle_flip_state():
     ok = ~np.isnan(d["x"]).any(axis=1)
     assert ok.sum() >= 13312 - 64  # the shipped state holds a few NaN rows (escaped particles); they are passed on as they are
     assert np.abs(d["x"][ok]).max() < 10 and (d["kappa"] <= 0).all()
+
+
+REF_SCENES = "/root/reference/experiments/rigid_body_trajectory_optimization/scene"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("scene,n_fluid,n_bodies,n_emitters", [
+    ("diff-stone-skipping.json", 237699, 2, 0),
+    ("diff-water-rafting-bunny.json", 105154, 2, 0),
+    ("diff-bottle-model-collide.json", 13312, 2, 0),
+    ("diff-high-diving-duck.json", 118389, 5, 1),
+])
+def test_paper_scenes_load_with_the_reference_particle_counts(scene, n_fluid, n_bodies, n_emitters):
+    """The four scenes of BASELINE.json configs[0..3] through the host loader: the fluid lattices reproduce the particle
+    counts of the reference's logs exactly (createFluidBlocks), every mesh is found and sampled."""
+    sph = import_sph()
+    d = sph._load_scene_summary(os.path.join(REF_SCENES, scene))
+    assert d["num_fluid"] == n_fluid
+    assert len(d["bodies"]) == n_bodies and d["num_emitters"] == n_emitters
+    assert all(b["num_particles"] > 100 for b in d["bodies"])
+    assert sum(1 for b in d["bodies"] if b["dynamic"]) == 1
