@@ -349,6 +349,23 @@ PYBIND11_MODULE(_core, m) {
     }
     d["bodies"] = bodies;
     d["num_emitters"] = sc.emitters.size();
+    py::list emitters;  // keyword arguments of difffr_b200.cabi.Context.add_emitter
+    for (const EmitterDesc &e : sc.emitters) {
+      py::dict ed;
+      double R[9];
+      quat_to_matrix(e.rotation, R);
+      py::array_t<double> rot(9);
+      std::memcpy(rot.mutable_data(), R, sizeof(R));
+      ed["width"] = e.width;
+      ed["height"] = e.height;
+      ed["position"] = np_vec3(e.x);
+      ed["rotation"] = rot;
+      ed["velocity"] = e.velocity;
+      ed["emit_start"] = e.emit_start;
+      ed["emit_end"] = e.emit_end;
+      emitters.append(ed);
+    }
+    d["emitters"] = emitters;
     return d;
   }, "scene_file"_a, "param"_a = "");
 }

@@ -62,3 +62,56 @@ assert worst < 1e-9
 ''' % (ROOT, os.path.join(ROOT, "oracle", "liboracle.so"), os.path.join(ROOT, "oracle", "_ref", "libref.so"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+REF_SCENES = "/root/reference/experiments/rigid_body_trajectory_optimization/scene"
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref.so")) and os.path.isdir(REF_SCENES)),
+                    reason="oracle/_ref not built / reference checkout absent (build container only)")
+def test_oracle_against_live_reference_on_the_high_diving_scene():
+    """BASELINE.json configs[3]'s scene (diff-high-diving-duck.json: 118,389 fluid particles, the duck, four static meshes
+    with 293 k samples, a box emitter that fires in the first step) through the host loader, then step by step through the
+    reference's own translation units and the oracle.  No fixture for this one (the boundary samples alone are 7 MB)."""
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes, os, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from pysph_util import import_sph
+from difffr_b200.cabi import Config, Context
+sph = import_sph()
+sc = sph._load_scene_full(os.path.join(%r, "diff-high-diving-duck.json"), "")
+assert sc["num_emitters"] == 1
+olib = ctypes.CDLL(%r); rlib = ctypes.CDLL(%r)
+def build(lib, prefix):
+    ctx = Context(config=Config.from_buffer_copy(sc["config"]), lib=lib, prefix=prefix)
+    ctx.set_fluid(sc["fluid_x"], sc["fluid_v"])
+    for b in sc["bodies"]:
+        ctx.add_body(b["samples"], bool(b["dynamic"]), float(b["density"]), b["translation"], b["rotation"])
+    for e in sc["emitters"]:
+        ctx.add_emitter(**e)
+    for i, b in enumerate(sc["bodies"]):
+        if b["dynamic"]: ctx.set_init_v_omega(i, b["init_v"], b["init_omega"])
+    ctx.finalize()
+    return ctx
+o, r = build(olib, "orc_"), build(rlib, "ref_")
+dyn = [i for i, b in enumerate(sc["bodies"]) if b["dynamic"]][0]
+def rel(a, b): return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+worst = 0.0
+n0 = o.num_fluid
+for s in range(6):
+    o.step(1); r.step(1)
+    io, ir = o.step_info(), r.step_info()
+    assert (io.iterations, io.iterations_v, io.num_fluid_particles) == (ir.iterations, ir.iterations_v, ir.num_fluid_particles), (s, io.iterations, ir.iterations)
+    for f in ("position", "velocity", "density", "kappa"): worst = max(worst, rel(o.fluid(f), r.fluid(f)))
+    so, sr = o.body_state(dyn), r.body_state(dyn)
+    for k in so: worst = max(worst, rel(so[k], sr[k]))
+    for w in range(16): worst = max(worst, rel(o.body_grad(dyn, w), r.body_grad(dyn, w)))
+assert o.step_info().num_fluid_particles > n0, "the emitter fired"
+print("WORST", worst)
+assert worst < 1e-9
+''' % (ROOT, ROOT, REF_SCENES, os.path.join(ROOT, "oracle", "liboracle.so"), os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
