@@ -1343,7 +1343,8 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
     const double h2s = P.support_radius * P.support_radius;
     // (x_j, rho_j) comes as one record (xrho); the normal and the velocity are gathered only when their
     // force is switched on
-    for_neighbors4<DFR_NP_U>(
+    for_neighbors4<2>(  // two gather triples in flight (the standalone pass has the registers for it)
+       
         lf, i, i,
         [&](int j) {
           Rec3 q;
