@@ -118,7 +118,7 @@ class TimeStepDiffDFSPH {
   unsigned int get_step_count() const;
   void add_log(const std::string &s);
   void reset_gradient();
-  unsigned int get_num_1ring_fluid_particle() const { return 0; }
+  unsigned int get_num_1ring_fluid_particle() const;
   unsigned int getIterations() const;   // TimeStep::SOLVER_ITERATIONS
   unsigned int getIterationsV() const;  // TimeStepDiffDFSPH::SOLVER_ITERATIONS_V
 
@@ -570,6 +570,25 @@ inline Quat TimeStepDiffDFSPH::get_target_quaternion_vec4(unsigned int i) const 
   return quat_from_euler_deg(base->getScene().bodies.at(i).target_angle_deg);  // SimulationDataDiffDFSPH.h:169-185
 }
 inline unsigned int TimeStepDiffDFSPH::get_step_count() const { return (unsigned int)base->info().step_count; }
+// TimeStepDiffDFSPH::countNeighborDOF (TimeStepDiffDFSPH.cpp:283-350, getter :2242): fluid particles that have at least
+// one neighbour among the particles of a dynamic (or animated) body, summed over those bodies.  The reference counts
+// this inside step() when `enable count neighbor dof` is set; here it is evaluated on demand from the fluid -> body
+// neighbour sets of the current positions (a diagnostic of experiments/others/python/grad-sensitivity-1ring.py).
+inline unsigned int TimeStepDiffDFSPH::get_num_1ring_fluid_particle() const {
+  dfr_context *ctx = base->context();
+  if (!ctx) return 0;
+  const int64_t n = dfr_num_fluid(ctx);
+  std::vector<int32_t> counts((size_t)std::max<int64_t>(n, 1));
+  unsigned int total = 0;
+  const auto &bodies = base->getScene().bodies;
+  for (size_t b = 0; b < bodies.size(); b++) {
+    if (!bodies[b].dynamic) continue;
+    int64_t entries = 0;
+    base->check(dfr_get_neighbors(ctx, -1, (int)b, counts.data(), nullptr, 0, &entries));
+    for (int64_t i = 0; i < n; i++) total += counts[(size_t)i] > 0 ? 1u : 0u;
+  }
+  return total;
+}
 inline unsigned int TimeStepDiffDFSPH::getIterations() const { return (unsigned int)base->info().iterations; }
 inline unsigned int TimeStepDiffDFSPH::getIterationsV() const { return (unsigned int)base->info().iterations_v; }
 inline void TimeStepDiffDFSPH::add_log(const std::string &s) { base->log(s); }

@@ -31,6 +31,7 @@ def run_script_like(sph, scene_path, out_dir, n_iterations=2, gradient_mode=1):
             x=bm.get_position_rb(), q=bm.get_quaternion_rb_vec4(), v=bm.get_velocity_rb(), w=bm.get_angular_velocity_rb(),
             gx_v=bm.get_grad_x_to_v0(), gx_w=bm.get_grad_x_to_omega0(), gq_v=bm.get_grad_quaternion_to_v0(),
             gq_w=bm.get_grad_quaternion_to_omega0(), steps=timestep.get_step_count(), t=sph.TimeManager.getCurrent().getTime(),
+            n_1ring=timestep.get_num_1ring_fluid_particle(),
         )
         records.append(rec)
         timestep.set_loss(float(np.sum((rec["x"] - timestep.get_target_x(1)) ** 2)))
@@ -83,6 +84,10 @@ def test_script_flow_reproduces_itself_and_the_oracle(tmp_path, oracle_factory):
     orc.finalize()
     n_orc = orc.run_trajectory(10000)
     assert n_orc == a["steps"]
+    # countNeighborDOF (TimeStepDiffDFSPH.cpp:283-350): fluid particles with a neighbour on the dynamic body, from the
+    # oracle's fluid -> body neighbour sets at the end of the trajectory
+    cnt, _ = orc.neighbors(-1, 1)
+    assert a["n_1ring"] == b["n_1ring"] == int((cnt > 0).sum()) > 0
     so = orc.body_state(1)
     assert rel_err(a["x"], so["x"]) < 1e-6 and rel_err(a["q"], so["q"]) < 1e-6
     assert rel_err(a["v"], so["v"]) < 1e-6 and rel_err(a["w"], so["omega"]) < 1e-6
