@@ -14,6 +14,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <sys/stat.h>
 
 #include "scene_host.hpp"
@@ -156,6 +157,7 @@ class Simulation {
   bool useRigidContactSolver() const;
   double getParticleRadius() const;
   double getSupportRadius() const;
+  SimulatorBase *simulatorBase() const { return base; }
   static Simulation *current;
 
  private:
@@ -419,6 +421,25 @@ class SimulatorBase {
   }
   double wall_ms_steps = 0.0;
   long long steps_taken = 0;
+  // Utilities::Timing::printAverageTimes / printTimeSums (opt-ng.py:178-179): the reference prints the START_TIMING
+  // averages of its phases; here one line for the host wall time of a step and one for the device time
+  std::string timing_report(bool sums) const {
+    std::ostringstream os;
+    const double n = (double)std::max<long long>(steps_taken, 1);
+    double dev_ms = 0.0;
+    int64_t launches = 0;
+    if (ctx) dfr_get_device_time_ms(ctx, &dev_ms, &launches);
+    os << "---------------------------------------------------------------------------\n";
+    if (sums) {
+      os << "Time sums:\n  timeStepNoGUI (host wall, read-back included): " << wall_ms_steps << " ms over " << steps_taken << " steps\n"
+         << "  device (CUDA events around dfr_step): " << dev_ms << " ms, " << launches << " kernel launches\n";
+    } else {
+      os << "Average times:\n  timeStepNoGUI (host wall, read-back included): " << wall_ms_steps / n << " ms\n"
+         << "  device (CUDA events around dfr_step): " << dev_ms / n << " ms, " << (double)launches / n << " kernel launches per step\n";
+    }
+    os << "---------------------------------------------------------------------------\n";
+    return os.str();
+  }
 
  private:
   void build_context() {

@@ -256,8 +256,12 @@ PYBIND11_MODULE(_core, m) {
   py::module_ util = m.def_submodule("Utilities");
   struct TimingStub {};
   py::class_<TimingStub>(util, "Timing")
-      .def_static("printAverageTimes", []() {})
-      .def_static("printTimeSums", []() {})
+      .def_static("printAverageTimes", []() {
+        if (Simulation::current) py::print(Simulation::current->simulatorBase()->timing_report(false));
+      })
+      .def_static("printTimeSums", []() {
+        if (Simulation::current) py::print(Simulation::current->simulatorBase()->timing_report(true));
+      })
       .def_static("reset", []() {});
 
   // partio .bgeo fluid state files (host/state_io.hpp), exposed for tests and for exporting settled states

@@ -43,6 +43,8 @@ def run_script_like(sph, scene_path, out_dir, n_iterations=2, gradient_mode=1):
 
     base.setTimeStepCB(time_step_callback)
     base.runSimulation()
+    sph.Utilities.Timing.printAverageTimes()  # opt-ng.py:178-179
+    sph.Utilities.Timing.printTimeSums()
     base.cleanup()
     return records
 
