@@ -419,16 +419,15 @@ class SimulatorBase {
       std::fflush(log_file);
     }
   }
-  double wall_ms_steps = 0.0;
-  long long steps_taken = 0;
+  double wall_ms_steps = 0.0, device_ms_steps = 0.0;
+  long long steps_taken = 0, launches_steps = 0;
   // Utilities::Timing::printAverageTimes / printTimeSums (opt-ng.py:178-179): the reference prints the START_TIMING
   // averages of its phases; here one line for the host wall time of a step and one for the device time
   std::string timing_report(bool sums) const {
     std::ostringstream os;
     const double n = (double)std::max<long long>(steps_taken, 1);
-    double dev_ms = 0.0;
-    int64_t launches = 0;
-    if (ctx) dfr_get_device_time_ms(ctx, &dev_ms, &launches);
+    const double dev_ms = device_ms_steps;
+    const long long launches = launches_steps;
     os << "---------------------------------------------------------------------------\n";
     if (sums) {
       os << "Time sums:\n  timeStepNoGUI (host wall, read-back included): " << wall_ms_steps << " ms over " << steps_taken << " steps\n"
@@ -468,7 +467,13 @@ class SimulatorBase {
     deferredInit();
     if (callbacks && step_cb_before) step_cb_before();
     const auto t0 = std::chrono::steady_clock::now();
+    double dev0 = 0.0, dev1 = 0.0;
+    int64_t l0 = 0, l1 = 0;
+    dfr_get_device_time_ms(ctx, &dev0, &l0);  // cumulative since the last reset
     check(dfr_step(ctx, 1));
+    dfr_get_device_time_ms(ctx, &dev1, &l1);
+    device_ms_steps += dev1 - dev0;
+    launches_steps += l1 - l0;
     wall_ms_steps += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     steps_taken++;
     info_valid = false;
