@@ -80,7 +80,10 @@ typedef struct dfr_config {
   double target_time;              /* "targetTime" */
   double uniform_acc_rb_time;      /* "uniformAccelerateRBTime" */
   int32_t max_emitted_particles;   /* capacity reserved for emitters (Emitter.cpp) */
-  /* Device-side tuning (0 = default).  These have no counterpart in the reference; they never change results. */
+  /* Device-side tuning (0 = default).  These have no counterpart in the reference; they never change results.
+   * The three capacities are INITIAL values: rows that do not fit make the context grow them and rebuild the lists
+   * before the step continues (the reference's lists are unbounded); DFR_ERR_CAPACITY is only left for a row that
+   * more than doubles within one step outside the first steps after finalize / reset / load, and for slab contexts. */
   int32_t neighbor_capacity_fluid;    /* fluid neighbours stored per fluid particle (default 96) */
   int32_t neighbor_capacity_boundary; /* boundary neighbours stored per fluid particle (default 64) */
   int32_t body_neighbor_capacity;     /* mean fluid neighbours stored per dynamic boundary particle (default 96) */
@@ -110,7 +113,9 @@ int dfr_add_body(dfr_context *ctx, int64_t n, const double *x_local, int is_dyna
                  double density, const double position[3], const double quat_wxyz[4]);
 
 /* Per-body targets / initial velocities: SimulationDataDiffDFSPH get_init_v_rb / get_init_omega_rb
- * (DiffDFSPHModule.cpp:60-75; TimeStepDiffDFSPH.cpp:2087-2095). */
+ * (DiffDFSPHModule.cpp:60-75; TimeStepDiffDFSPH.cpp:2087-2095).  After dfr_finalize the values are staged and reach the
+ * device in stream order at the start of the next dfr_step / dfr_run_trajectory (or with dfr_reset): the call itself
+ * never synchronises, so it can be made every step (controller experiments). */
 int dfr_set_init_v_omega(dfr_context *ctx, int body, const double v0[3], const double omega0[3]);
 
 /* Slab domain decomposition of one scene over the GPUs of a node (nothing comparable in the reference,
