@@ -322,6 +322,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     ctx.load_fluid_state(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())  # also resets the context
+    t_load = time.perf_counter() - t0
     d2h = 0
     for k in range(e2e_steps):
         for b in dyn:
@@ -465,7 +466,7 @@ def main():
         "solver": {"mean_neighbors": nbar, "divergence_iters": D, "pressure_iters": P, "h": i1.time_step_size},
         "clocks": clocks,
         "e2e": {"value": e2e_psteps_all / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_per_step,
-                "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms / e2e_steps,
+                "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms / e2e_steps, "load_state_ms_rank0": 1e3 * t_load,
                 "what": "dfr_load_fluid_state from pinned host arrays + per step: dfr_set_init_v_omega, dfr_step(1), "
                         "dfr_get_body_state + 8x dfr_get_body_grad per dynamic body"},
         "gpu_launches": int(launches_all),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dfr.h"
@@ -143,6 +144,8 @@ struct dfr_context {
     DevBuf<double4> s_pos[2], s_vel[2], s_misc[2], r_misc;
     DevBuf<int> counts;                  // [0..1] my export counts, [2..3] what the neighbours export to me
     int *h_counts = nullptr;             // pinned, 4 ints
+    double *h_stage = nullptr;           // pinned staging of dfr_load_fluid_state (10 doubles per local particle)
+    size_t h_stage_n = 0;
     DevBuf<double> body_buf;
     long long exchanged_bytes = 0;       // NVLink traffic of the steps since reset (both directions, this rank)
     // peer-memory transport of the ghost updates (cudaIpc-mapped neighbour buffers, NVLink stores from the producing
@@ -1311,6 +1314,7 @@ void dfr_destroy(dfr_context *c) {
     if (p) cudaIpcCloseMemHandle(p);
   c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free(); c->slab.flags.free(); c->slab.ipc_stage.free();
   if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
+  if (c->slab.h_stage) cudaFreeHost(c->slab.h_stage);
   if (c->slab.comm && nccl_api(nullptr)) nccl_api(nullptr)->CommDestroy(c->slab.comm);
   c->c_vol0.free(); c->c_dens0.free(); c->c_dens.free(); c->c_records.free(); c->c_vel.free(); c->c_order.free();
   for (auto &p : c->prof_pending) {
@@ -1651,6 +1655,15 @@ int dfr_finalize(dfr_context *c) {
     if (cudaMallocHost((void **)&S.h_counts, 8 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   }
   c->slab_needs_p2p_setup = c->slab.on;
+  if (c->slab.on && c->nf_loc0 > 0 && c->slab.h_stage_n < (size_t)c->nf_loc0) {
+    // pinned staging of dfr_load_fluid_state, allocated here so that a load never pays for the (slow) pinned allocation
+    if (c->slab.h_stage) cudaFreeHost(c->slab.h_stage);
+    c->slab.h_stage = nullptr;
+    c->slab.h_stage_n = 0;
+    if (cudaMallocHost((void **)&c->slab.h_stage, (size_t)c->nf_loc0 * 10 * sizeof(double)) != cudaSuccess)
+      return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
+    c->slab.h_stage_n = (size_t)c->nf_loc0;
+  }
   CU(c->dEmitters.alloc(std::max<size_t>(c->h_emitters.size(), 1)));
   const int nc = P.grid.ncells;
   CU(c->dSt.alloc(1));
@@ -1792,24 +1805,40 @@ int dfr_load_fluid_state(dfr_context *c, const double *x, const double *v, const
     CU(cudaStreamSynchronize(c->stream));
     return reset_device_state(c);
   }
-  auto id_of = [&](int64_t k) { return c->slab.on ? (int64_t)c->h_ids0[k] : k; };
-  std::vector<double4> tmp(n);
-  std::vector<double> tmp1(n);
-  if (x) {
-    for (int64_t k = 0; k < n; k++) tmp[k] = make_double4(x[3 * id_of(k)], x[3 * id_of(k) + 1], x[3 * id_of(k) + 2], 0.0);
-    CU(cudaMemcpy(c->pos_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
-  }
-  if (v) {
-    for (int64_t k = 0; k < n; k++) tmp[k] = make_double4(v[3 * id_of(k)], v[3 * id_of(k) + 1], v[3 * id_of(k) + 2], 0.0);
-    CU(cudaMemcpy(c->vel_init.p, tmp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
-  }
-  if (kappa) {
-    for (int64_t k = 0; k < n; k++) tmp1[k] = kappa[id_of(k)];
-    CU(cudaMemcpy(c->kappa_init.p, tmp1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  }
-  if (kappa_v) {
-    for (int64_t k = 0; k < n; k++) tmp1[k] = kappa_v[id_of(k)];
-    CU(cudaMemcpy(c->kappav_init.p, tmp1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  // slab: this rank keeps the ids it owned at t = 0.  The rows are gathered by a few host threads into a pinned staging
+  // buffer and copied asynchronously (a single-threaded gather into pageable vectors + blocking copies cost ~35 ms per
+  // million particles, i.e. most of a short trajectory's end-to-end time)
+  if (n > 0) {
+    if (c->slab.h_stage_n < (size_t)n) {
+      if (c->slab.h_stage) cudaFreeHost(c->slab.h_stage);
+      c->slab.h_stage = nullptr;
+      if (cudaMallocHost((void **)&c->slab.h_stage, (size_t)n * 10 * sizeof(double)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
+      c->slab.h_stage_n = (size_t)n;
+    }
+    double4 *sx = reinterpret_cast<double4 *>(c->slab.h_stage);  // n double4 | n double4 | n double | n double
+    double4 *sv = sx + n;
+    double *sk = reinterpret_cast<double *>(sv + n);
+    double *skv = sk + n;
+    const int *ids = c->h_ids0.data();
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(8, n / 65536));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+      pool.emplace_back([=]() {
+        const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+        for (int64_t k = lo; k < hi; k++) {
+          const int64_t id = ids[k];
+          if (x) sx[k] = make_double4(x[3 * id], x[3 * id + 1], x[3 * id + 2], 0.0);
+          if (v) sv[k] = make_double4(v[3 * id], v[3 * id + 1], v[3 * id + 2], 0.0);
+          if (kappa) sk[k] = kappa[id];
+          if (kappa_v) skv[k] = kappa_v[id];
+        }
+      });
+    for (auto &th : pool) th.join();
+    if (x) CU(cudaMemcpyAsync(c->pos_init.p, sx, n * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+    if (v) CU(cudaMemcpyAsync(c->vel_init.p, sv, n * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+    if (kappa) CU(cudaMemcpyAsync(c->kappa_init.p, sk, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (kappa_v) CU(cudaMemcpyAsync(c->kappav_init.p, skv, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
   }
   // like the oracle, loading re-bases the running state: positions/velocities/kappas are replaced in id order
   return reset_device_state(c);

@@ -54,6 +54,15 @@ def main():
             slab.reset()
             if single:
                 single.reset()
+        if s == steps // 2 + 1:  # load a state (id order, whole scene on every rank): each slab keeps its own rows
+            rng = np.random.default_rng(17)
+            st_x = sc["fluid"] + rng.uniform(-0.1, 0.1, size=sc["fluid"].shape) * sc["radius"]
+            st_v = rng.normal(scale=0.1, size=sc["fluid"].shape)
+            st_k = -1e-6 * rng.random(n)
+            st_kv = -1e-3 * rng.random(n)
+            slab.load_fluid_state(st_x, st_v, st_k, st_kv)
+            if single:
+                single.load_fluid_state(st_x, st_v, st_k, st_kv)
         slab.step(1)
         info = slab.step_info()
         owned = torch.tensor([info.num_fluid_particles], dtype=torch.int64)
