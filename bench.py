@@ -161,13 +161,37 @@ class quiet_stdout:
         os.close(self.null)
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def use_all_host_threads():
+    """The CPU arm uses every host core it may run on.  torch.distributed.run injects OMP_NUM_THREADS=1 into every rank;
+    that value is replaced before the OpenMP runtime of the CPU library reads it, and the runtime is told again after
+    loading (it may already be mapped by another module)."""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
+
+
 def cpu_arm(lib_path, prefix, scene, steps, warmup):
     """Time the CPU implementation (oracle port or oracle/_ref) on `scene`; returns (particle-steps/s, cores, ms/step, info)."""
     from difffr_b200 import scenes
     from difffr_b200.cabi import Context
 
+    n_threads = use_all_host_threads()
     with quiet_stdout():
         lib = ctypes.CDLL(lib_path)
+        try:
+            gomp = ctypes.CDLL("libgomp.so.1")
+            gomp.omp_set_dynamic(0)
+            gomp.omp_set_num_threads(n_threads)
+        except OSError:
+            pass
         ctx = scenes.build_context(lambda **k: Context(lib=lib, prefix=prefix, **k), scene, **CFG)
         cores = 1
         if hasattr(lib, prefix + "num_threads"):
@@ -202,14 +226,21 @@ def reference_arm(args, rank, world):
     n_ref = int(min(N_PARTICLES, max(20000, budget_particle_steps / max(args.steps + args.warmup, 1))))
     scene = make_scene(n_ref)
     value, cores, ms, info = cpu_arm(lib_path, prefix, scene, args.steps, args.warmup)
-    sample = (f"{args.steps} steps (+{args.warmup} warm-up) of the dam break with {len(scene['fluid'])} fluid particles "
-              f"({'the full workload' if len(scene['fluid']) >= N_PARTICLES * 0.99 else 'same scene family, reduced size'}), FP64, OpenMP")
+    nfl = len(scene['fluid'])
+    if args.gpus > 1 and args.mode == "slab":
+        rel = (f"bounded sample of the workload: the {args.gpus} x {N_PARTICLES}-particle scene of `config` is {args.gpus} x this one; "
+               f"the CPU code's per-particle cost does not depend on the scene size, so particle-steps/s carry over")
+    else:
+        rel = "the full workload" if nfl >= N_PARTICLES * 0.99 else "same scene family, reduced size"
+    sample = (f"{args.steps} steps (+{args.warmup} warm-up) of the dam break with {nfl} fluid particles ({rel}), FP64, "
+              f"OpenMP on {cores} threads")
     line = {
         "impl": "reference", "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, args.mode),
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "sample_fluid_particles": nfl, "host_cores": host_cores()},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -93,7 +93,7 @@ SYMBOLS = [
     "default_config", "create", "destroy", "last_error", "set_fluid", "add_body",
     "set_init_v_omega", "finalize", "load_fluid_state", "reset", "step", "run_trajectory",
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
-    "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid",
+    "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid", "num_fluid_initial",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
     "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_plan", "slab_unique_id", "slab_configure", "slab_info",
 ]
@@ -220,6 +220,7 @@ class Context:
         proto("download_fluid", C.c_int, vp, C.c_int, dp)
         proto("download_body", C.c_int, vp, C.c_int, C.c_int, dp)
         proto("num_fluid", i64, vp)
+        proto("num_fluid_initial", i64, vp)
         proto("num_body_particles", i64, vp, C.c_int)
         proto("num_bodies", C.c_int, vp)
         proto("get_neighbors", C.c_int, vp, C.c_int, C.c_int, ip, ip, i64, C.POINTER(i64))
@@ -303,6 +304,11 @@ class Context:
 
     def load_fluid_state(self, x=None, v=None, kappa=None, kappa_v=None):
         x, v, k, kv = _f64(x), _f64(v), _f64(kappa), _f64(kappa_v)
+        # dfr_load_fluid_state takes no count: it reads the scene's initial particle count from every array it is given
+        n = int(self._fn("num_fluid_initial")(self._ctx))
+        for name, a, width in (("x", x, 3), ("v", v, 3), ("kappa", k, 1), ("kappa_v", kv, 1)):
+            if a is not None and a.size != width * n:
+                raise ValueError(f"load_fluid_state: {name} holds {a.size} values, the scene's {n} fluid particles need {width * n}")
         self._check(self._fn("load_fluid_state")(self._ctx, _dptr(x), _dptr(v), _dptr(k), _dptr(kv)))
 
     # -- stepping -------------------------------------------------------------------------

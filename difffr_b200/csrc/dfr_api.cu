@@ -49,7 +49,11 @@ struct DevBuf {
     n = count;
     if (count == 0) return cudaSuccess;
     cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    // The clear runs on the legacy default stream and may return before the device has done it; the context's stream
+    // is non-blocking, i.e. not ordered against that stream, so wait here - a kernel enqueued right after a (re)allocation
+    // must not race with the clear (allocations only happen at finalize and when a capacity grows)
     if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
   }
   void free() {
@@ -1507,6 +1511,13 @@ int dfr_finalize(dfr_context *c) {
   P.target_time = cfg.target_time; P.uniform_acc_time = cfg.uniform_acc_rb_time;
   P.time_step_size0 = cfg.time_step_size;
   P.n_bodies = (int)c->bodies.size();
+  // Viscosity_Standard::step (Viscosity_Standard.cpp:273-300) applies the boundary-viscosity reaction force (and, with
+  // BACKWARD, its Jacobian) to the neighbouring body; this path only applies the acceleration to the fluid, which is the
+  // whole effect for static bodies but would silently break momentum exchange and sensitivities of a dynamic one
+  if (cfg.viscosity_boundary != 0.0 && cfg.viscosity_method == 1)
+    for (const auto &hb : c->bodies)
+      if (hb.dynamic)
+        return fail(c, DFR_ERR_INVALID, "viscosityBoundary != 0 with a dynamic rigid body: the reaction force on the body is not on this path");
 
   // ---- boundary layout: static bodies first, then dynamic ----
   int off = 0;
@@ -2067,6 +2078,7 @@ int64_t dfr_num_fluid(dfr_context *c) {
   if (sync_state(c)) return 0;
   return c->slab.on ? c->nf0 : c->hSt->nf;  // arrays of the parity dumps are indexed by the scene's particle ids
 }
+int64_t dfr_num_fluid_initial(dfr_context *c) { return c ? c->nf0 : 0; }
 int64_t dfr_num_body_particles(dfr_context *c, int body) {
   return (c && body >= 0 && body < (int)c->bodies.size()) ? c->bodies[body].n : 0;
 }

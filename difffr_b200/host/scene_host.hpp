@@ -242,7 +242,18 @@ inline Scene load_scene(const std::string &scene_file, const std::string &param 
     int bh = 0;
     if (cfg->read("boundaryHandlingMethod", bh) && bh != 0)
       throw std::runtime_error("only Akinci2012 boundary handling (boundaryHandlingMethod 0) is provided by this module");
+    // 2-D scenes use 2-D kernels, particle volumes and the 7-neighbour deficiency cut (Simulation.cpp:382-386,
+    // TimeStepDiffDFSPH.cpp:2027-2040): not on this path, and running them as 3-D would be silently wrong
+    bool sim2d = false;
+    if (cfg->read("sim2D", sim2d) && sim2d) throw std::runtime_error("sim2D scenes are outside this path (3-D DiffDFSPH only)");
   }
+  // articulated systems / joints (ArticulatedSystemSimulator.cpp) and particle-file fluids are not on this path
+  if (const Json *as = root.find("ArticulatedSystems"))
+    if (!as->arr.empty()) throw std::runtime_error("ArticulatedSystems (joints) are outside this path");
+  if (const Json *js = root.find("Joints"))
+    if (!js->arr.empty()) throw std::runtime_error("Joints are outside this path");
+  if (const Json *fm = root.find("FluidModels"))
+    if (!fm->arr.empty()) throw std::runtime_error("FluidModels (particle-file fluids) are outside this path; use FluidBlocks or a state file");
   if (const Json *mats = root.find("Materials"))
     for (const Json &m : mats->arr) {
       std::string id = "Fluid";
@@ -305,6 +316,9 @@ inline Scene load_scene(const std::string &scene_file, const std::string &param 
       b.scale = {s3[0], s3[1], s3[2]};
       rb.read("isDynamic", b.dynamic);
       rb.read("isWall", b.is_wall);
+      bool animated = false;
+      if (rb.read("isAnimated", animated) && animated)
+        throw std::runtime_error("animated rigid bodies (isAnimated) are outside this path");
       double v3[3];
       if (rb.read_vec("targetX", v3)) b.target_x = {v3[0], v3[1], v3[2]};
       if (rb.read_vec("targetAngleInDegree", v3)) b.target_angle_deg = {v3[0], v3[1], v3[2]};

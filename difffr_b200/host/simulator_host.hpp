@@ -349,8 +349,10 @@ class SimulatorBase {
                     std::fread(k.data(), sizeof(double), k.size(), f) == k.size() && std::fread(kv.data(), sizeof(double), kv.size(), f) == kv.size();
     std::fclose(f);
     if (!rd) throw std::runtime_error("state file " + path + " is truncated");
-    check(dfr_load_fluid_state(ctx, x.data(), mode >= 2 || mode == 0 ? v.data() : nullptr, mode == 0 ? k.data() : nullptr,
-                               mode == 0 ? kv.data() : nullptr));
+    // same semantics as the .bgeo branch: every field of the file is loaded, --load-fluid-pos then clears the velocities
+    // (loadFluidParticlePositions -> clearVelocities, SimulatorBase.cpp:2043-2058)
+    if (mode == 1) std::fill(v.begin(), v.end(), 0.0);
+    check(dfr_load_fluid_state(ctx, x.data(), v.data(), k.data(), kv.data()));
     info_valid = false;
     step_serial++;
   }

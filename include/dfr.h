@@ -217,6 +217,9 @@ int dfr_download_fluid(dfr_context *ctx, int field, double *out);
 /*   field: 0 position (3) 1 velocity (3) 2 volume 3 position0 (3); n = particles of that body */
 int dfr_download_body(dfr_context *ctx, int body, int field, double *out);
 int64_t dfr_num_fluid(dfr_context *ctx);
+/* Fluid particles of the scene as given to dfr_set_fluid (FluidModel::numParticles() before any emission): the length
+ * (in particles) dfr_load_fluid_state expects of its arrays. */
+int64_t dfr_num_fluid_initial(dfr_context *ctx);
 int64_t dfr_num_body_particles(dfr_context *ctx, int body);
 int dfr_num_bodies(dfr_context *ctx);
 

@@ -1881,6 +1881,7 @@ int orc_download_body(dfr_context *c, int body, int field, double *out) {
   return DFR_OK;
 }
 int64_t orc_num_fluid(dfr_context *c) { return c ? c->nf : 0; }
+int64_t orc_num_fluid_initial(dfr_context *c) { return c ? c->nfActive0 : 0; }
 int64_t orc_num_body_particles(dfr_context *c, int body) { return (c && body >= 0 && body < (int)c->bodies.size()) ? c->bodies[body].n : 0; }
 int orc_num_bodies(dfr_context *c) { return c ? (int)c->bodies.size() : 0; }
 

@@ -631,6 +631,7 @@ int64_t ref_num_fluid(dfr_context *c) {
   if (!c->finalized) return (int64_t)c->fx.size();
   return Simulation::getCurrent()->getFluidModel(0)->numActiveParticles();
 }
+int64_t ref_num_fluid_initial(dfr_context *c) { return c ? (int64_t)c->fx.size() : 0; }
 int64_t ref_num_body_particles(dfr_context *c, int body) {
   return (c && body >= 0 && body < (int)c->bodies.size()) ? (int64_t)c->bodies[body].x_local.size() : 0;
 }
