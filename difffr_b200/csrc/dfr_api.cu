@@ -69,7 +69,21 @@ struct dfr_context {
   dfr_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t ls = nullptr;  // the stream kernels are launched on: `stream`, or a capture stream while a step graph is recorded
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // CUDA-graph stepping: one instantiated graph per (gated?, buffer parity); see capture_step_graph
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    int64_t n_static = 0, n_div_body = 0, n_prs_body = 0;  // kernels per step / per solver iteration (launch accounting)
+  } step_graph[2][2];
+  bool capturing = false;
+  int graph_broken = 0;                 // a capture failed: stay on the stream path for good
+  cudaStream_t cap_stream[3] = {nullptr, nullptr, nullptr};
+  int cap_depth = 0;
+  unsigned long long cap_gate_handle = 0;
+  int64_t *cap_counter = nullptr;       // which of the StepGraph counters LAUNCH adds to while capturing
+  StepGraph *cap_target = nullptr;
   std::string err;
   bool finalized = false;
 
@@ -255,9 +269,10 @@ void prof_resolve(dfr_context *c, int used_div, int used_prs) {
   do {                                                             \
     if ((grid) > 0) {                                              \
       if ((c)->profiling) prof_begin((c), #kernel);                \
-      kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+      kernel<<<(grid), (block), 0, (c)->ls>>>(__VA_ARGS__);        \
       if ((c)->profiling) prof_end((c));                           \
-      (c)->launches++;                                             \
+      if ((c)->capturing) (*(c)->cap_counter)++;                   \
+      else (c)->launches++;                                        \
     }                                                              \
   } while (0)
 
@@ -292,9 +307,10 @@ int persistent_grid(dfr_context *c, K kernel, int nvb) {
     if ((nvb) > 0) {                                                                          \
       const int pg__ = persistent_grid((c), kernel, (nvb));                                   \
       if ((c)->profiling) prof_begin((c), #kernel);                                           \
-      kernel<<<pg__, 128, 0, (c)->stream>>>(__VA_ARGS__, next_sched((c), (nvb)));             \
+      kernel<<<pg__, 128, 0, (c)->ls>>>(__VA_ARGS__, next_sched((c), (nvb)));                 \
       if ((c)->profiling) prof_end((c));                                                      \
-      (c)->launches++;                                                                        \
+      if ((c)->capturing) (*(c)->cap_counter)++;                                              \
+      else (c)->launches++;                                                                   \
     }                                                                                         \
   } while (0)
 
@@ -390,7 +406,7 @@ NbrList list_b(dfr_context *c) {
 int build_dyn_grid(dfr_context *c) {
   if (c->n_dyn_p == 0) return DFR_OK;
   const int nc = c->P.grid.ncells;
-  cudaMemsetAsync(c->cell_start_d.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
+  cudaMemsetAsync(c->cell_start_d.p, 0, sizeof(unsigned int) * (nc + 1), c->ls);
   LAUNCH(c, k_bin_count, cdiv(c->n_dyn_p, 128), 128, c->P, c->bpos.p + c->dyn_begin, (const int *)nullptr, c->n_dyn_p,
          c->cell_start_d.p, c->cell_of_b.p, c->rank_b.p);
   int rc = scan_u32(c, c->cell_start_d.p, (size_t)nc + 1, nullptr);
@@ -415,7 +431,7 @@ int build_neighbors(dfr_context *c) {
     return build_neighbor_lists(c);
   }
   const int a = c->cur, b = 1 - c->cur;
-  cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->stream);
+  cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->ls);
   LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->P, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
   int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
   if (rc) return rc;
@@ -439,7 +455,7 @@ int build_neighbor_lists(dfr_context *c) {
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
          c->near_s.p);
   if (c->n_dyn_p > 0) {
-    cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->stream);
+    cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->ls);
     LAUNCH(c, k_dnbr_count, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
     rc = scan_u32(c, c->off_d.p, (size_t)c->n_dyn_p + 1, nullptr);
     if (rc) return rc;
@@ -468,6 +484,134 @@ int sync_state(dfr_context *c) {
     std::snprintf(buf, sizeof(buf), "neighbour list capacity exceeded (flags %d; longest rows f=%u b=%u, d entries=%u; cap f=%d b=%d d=%u)",
                   c->hSt->error_flags, c->hSt->list_used_f, c->hSt->list_used_b, c->hSt->list_used_d, c->cap_f, c->cap_b, c->cap_d);
     return fail(c, DFR_ERR_CAPACITY, buf);
+  }
+  return DFR_OK;
+}
+
+// ---- CUDA-graph stepping ---------------------------------------------------------------------------------------
+// A step is recorded once per buffer parity (the per-step re-sort flips pos/kappa/id buffers; the velocity buffer
+// flips twice per step) by stream capture of launch_step() and replayed with one cudaGraphLaunch.  The two Jacobi
+// loops are conditional WHILE nodes (condition written by k_residual_finish: TimeStepDiffDFSPH.cpp:711-743, 828-861),
+// and the whole step hangs in an IF node opened by k_step_gate, so that dfr_run_trajectory can enqueue steps in batches
+// without looking at `finished` after every one.  Nothing in a replayed step needs the host: no speculation, no
+// read-back between the solves.
+// Not recorded (the stream path below stays): slab-decomposed contexts (NCCL calls and host-side exchange sizes),
+// per-kernel profiling, steps in which the list capacities are being watched, DFR_NO_GRAPH=1.
+#define CUG(call)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      cudaGetLastError();                                                                                \
+      return fail(c, DFR_ERR_CUDA, std::string("step graph: ") + #call + ": " + cudaGetErrorString(e__)); \
+    }                                                                                                    \
+  } while (0)
+
+int launch_step(dfr_context *c);
+
+// A condition handle of the graph c->ls is recording into (value `default_value` at every launch of the graph).
+int cap_make_handle(dfr_context *c, unsigned int default_value, unsigned long long *handle_out) {
+  cudaStreamCaptureStatus status;
+  cudaGraph_t g = nullptr;
+  CUG(cudaStreamGetCaptureInfo_v2(c->ls, &status, nullptr, &g, nullptr, nullptr));
+  if (status != cudaStreamCaptureStatusActive) return fail(c, DFR_ERR_STATE, "step graph: stream is not capturing");
+  cudaGraphConditionalHandle h;
+  CUG(cudaGraphConditionalHandleCreate(&h, g, default_value, cudaGraphCondAssignDefault));
+  *handle_out = (unsigned long long)h;
+  return DFR_OK;
+}
+// Adds a conditional node after everything captured so far on c->ls and redirects the launches to its body graph.
+int cap_begin_conditional(dfr_context *c, cudaGraphConditionalNodeType type, unsigned long long handle) {
+  if (c->cap_depth + 1 >= 3) return fail(c, DFR_ERR_STATE, "step graph: conditional nodes nested too deep");
+  cudaStreamCaptureStatus status;
+  cudaGraph_t g = nullptr;
+  const cudaGraphNode_t *deps = nullptr;
+  size_t ndeps = 0;
+  CUG(cudaStreamGetCaptureInfo_v2(c->ls, &status, nullptr, &g, &deps, &ndeps));
+  if (status != cudaStreamCaptureStatusActive) return fail(c, DFR_ERR_STATE, "step graph: stream is not capturing");
+  const cudaGraphConditionalHandle h = (cudaGraphConditionalHandle)handle;
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.conditional.handle = h;
+  np.conditional.type = type;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  CUG(cudaGraphAddNode(&node, g, deps, ndeps, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  CUG(cudaStreamUpdateCaptureDependencies(c->ls, &node, 1, cudaStreamSetCaptureDependencies));
+  cudaStream_t bs = c->cap_stream[c->cap_depth + 1];
+  CUG(cudaStreamBeginCaptureToGraph(bs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  c->cap_depth++;
+  c->ls = bs;
+  return DFR_OK;
+}
+int cap_end_conditional(dfr_context *c) {
+  cudaGraph_t body = nullptr;
+  CUG(cudaStreamEndCapture(c->ls, &body));
+  c->cap_depth--;
+  c->ls = c->cap_stream[c->cap_depth];
+  return DFR_OK;
+}
+void drop_step_graphs(dfr_context *c) {
+  for (auto &row : c->step_graph)
+    for (auto &sg : row) {
+      if (sg.exec) cudaGraphExecDestroy(sg.exec);
+      if (sg.graph) cudaGraphDestroy(sg.graph);
+      sg = dfr_context::StepGraph();
+    }
+}
+bool graph_stepping_possible(const dfr_context *c) {
+  return !c->graph_broken && !c->slab.on && !c->profiling && getenv_int("DFR_NO_GRAPH") == 0 && getenv_int("DFR_NO_FUSION") != 3;
+}
+// Records the step that starts with buffer parity c->cur; `gated` = the step is skipped once the trajectory has finished.
+// Host-side buffer indices are restored afterwards (recording executes nothing).
+int capture_step_graph(dfr_context *c, int gated) {
+  dfr_context::StepGraph &sg = c->step_graph[gated][c->cur];
+  for (auto &cs : c->cap_stream)
+    if (!cs) CUG(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  const int cur0 = c->cur, vcur0 = c->vcur, parity0 = c->sched_parity;
+  sg = dfr_context::StepGraph();
+  c->capturing = true;
+  c->cap_target = &sg;
+  c->cap_counter = &sg.n_static;
+  c->cap_depth = 0;
+  c->ls = c->cap_stream[0];
+  int rc = DFR_OK;
+  cudaError_t e = cudaStreamBeginCapture(c->ls, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) rc = fail(c, DFR_ERR_CUDA, std::string("step graph: cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+  if (!rc && gated) {  // k_step_gate -> IF node holding the step
+    unsigned long long gate = 0;
+    rc = cap_make_handle(c, 1u, &gate);
+    if (!rc) {
+      k_step_gate<<<1, 1, 0, c->ls>>>(c->dSt.p, gate, 1);
+      rc = cap_begin_conditional(c, cudaGraphCondTypeIf, gate);
+    }
+    if (!rc) {
+      rc = launch_step(c);
+      if (!rc) rc = cap_end_conditional(c);
+    }
+  } else if (!rc)
+    rc = launch_step(c);
+  cudaGraph_t g = nullptr;
+  e = cudaStreamEndCapture(c->cap_stream[0], &g);
+  c->capturing = false;
+  c->cap_target = nullptr;
+  c->cap_counter = nullptr;
+  c->ls = c->stream;
+  c->cur = cur0;
+  c->vcur = vcur0;
+  c->sched_parity = parity0;
+  if (!rc && e != cudaSuccess) rc = fail(c, DFR_ERR_CUDA, std::string("step graph: cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  if (rc) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return rc;
+  }
+  sg.graph = g;
+  e = cudaGraphInstantiate(&sg.exec, g, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(g);
+    sg = dfr_context::StepGraph();
+    return fail(c, DFR_ERR_CUDA, std::string("step graph: cudaGraphInstantiate: ") + cudaGetErrorString(e));
   }
   return DFR_OK;
 }
@@ -826,6 +970,39 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
     PLAUNCH(c, (k_rho<PRESSURE, RHO_PLAIN>), g, RHO_ARGS);
   SLAB_SYNC(c, c->xk.p, sizeof(double4));
   const int max_it = PRESSURE ? c->cfg.max_iterations : c->cfg.max_iterations_v;
+  if (c->capturing) {
+    // graph stepping: the Jacobi iteration is the body of a WHILE node whose condition k_residual_finish writes - no
+    // speculation, no read-back.  With the fused non-pressure pass enabled both k_rho variants are in the body and the
+    // device decides per iteration which one runs (StepState::fuse_now).
+    unsigned long long cond = 0;
+    int64_t *outer_counter = c->cap_counter;
+    int rc = cap_make_handle(c, 1u, &cond);  // both solves run at least one iteration
+    if (!rc) rc = cap_begin_conditional(c, cudaGraphCondTypeWhile, cond);
+    if (rc) return rc;
+    c->cap_counter = PRESSURE ? &c->cap_target->n_prs_body : &c->cap_target->n_div_body;
+    launch_boundary_side<PRESSURE>(c, true, 1);
+    PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
+    const bool fuse_np = !PRESSURE && fuse_nonpressure;
+    if (fuse_np) {
+      RhoExtra X = X0;
+      X.normal = c->normal.p;
+      X.acc = c->acc.p;
+      X.gate = 1;
+      PLAUNCH(c, (k_rho<false, RHO_ITER, RHO_X_NONPRESSURE>), g, RHO_ARGS_X(c->xrho.p, X));
+      RhoExtra Xp = X0;
+      Xp.gate = 2;
+      PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS_X(c->pos[a].p, Xp));
+    } else
+      PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
+    LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
+           cond, fuse_np ? 1 : 0);
+    c->cap_counter = outer_counter;
+    // the two gated k_rho launches count as one executed kernel per iteration
+    if (fuse_np) c->cap_target->n_div_body -= 1;
+    rc = cap_end_conditional(c);
+    (void)max_it;
+    return rc;
+  }
   int launched = 0;
   int spec = PRESSURE ? c->spec_prs : c->spec_div;
   int fused_at = -1;  // iteration count at which the fused non-pressure pass ran
@@ -850,7 +1027,8 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
         fused_at = launched + spec;
       } else
         PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
-      LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS);
+      LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
+             0ull, 0);
       if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
@@ -1003,20 +1181,38 @@ int ensure_list_capacity(dfr_context *c) {
   return sync_state(c);  // reports the capacity error
 }
 
+// TimeStepDiffDFSPH::performNeighborhoodSearch (:2044-2056): z-sort of the contact order every 500 steps (host side:
+// a read-back of the dynamic particles, so it stays outside the step graph)
+int contact_sort_tick(dfr_context *c) {
+  if (!c->cfg.use_rigid_contact_solver) return DFR_OK;
+  if (c->sort_counter % 500 == 0) {
+    int rc = contact_sort_current(c);
+    if (rc) return rc;
+  }
+  c->sort_counter++;
+  return DFR_OK;
+}
+bool fuse_nonpressure_enabled(const dfr_context *c) {
+  const int no_fusion = getenv_int("DFR_NO_FUSION");
+  return c->cfg.enable_divergence_solver && c->cfg.use_divergence_warmstart && no_fusion != 1 && no_fusion != 2;
+}
+
+// Enqueues one step on c->ls.  While a step graph is being recorded (c->capturing) the host-side parts - contact order
+// sort, capacity watch - are left to the caller and the solver loops become WHILE nodes.
 int launch_step(dfr_context *c) {
   int n = c->launch_nf, g = cdiv(n, 128);
-  if (c->cfg.use_rigid_contact_solver) {  // TimeStepDiffDFSPH::performNeighborhoodSearch (:2044-2056): z-sort every 500 steps
-    if (c->sort_counter % 500 == 0) {
-      int rc = contact_sort_current(c);
-      if (rc) return rc;
-    }
-    c->sort_counter++;
+  int rc = DFR_OK;
+  if (!c->capturing) {
+    rc = contact_sort_tick(c);
+    if (rc) return rc;
   }
-  LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p);
-  int rc = build_neighbors(c);
+  LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, (c->capturing && fuse_nonpressure_enabled(c)) ? 1 : 0);
+  rc = build_neighbors(c);
   if (rc) return rc;
-  rc = ensure_list_capacity(c);
-  if (rc) return rc;
+  if (!c->capturing) {
+    rc = ensure_list_capacity(c);
+    if (rc) return rc;
+  }
   n = c->launch_nf;  // slab mode: the number of local particles changes with every exchange
   g = cdiv(n, 128);
   int a = c->cur;
@@ -1045,13 +1241,21 @@ int launch_step(dfr_context *c) {
     PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p, ghost_out(c, GA_NORMAL));
     SLAB_SYNC(c, c->normal.p, sizeof(double4));
   }
-  if (nonpressure_done)
+  if (c->capturing && fuse_nonpressure && c->cfg.enable_divergence_solver) {
+    // graph stepping: both are enqueued, StepState::np_done picks the one that runs (counted as one launch)
+    PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
+           c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p,
+           ghost_out(c, GA_VEL0 + (1 - c->vcur)), 1);
     LAUNCH(c, k_apply_accel, g, 128, c->dSt.p, c->acc.p, c->vel[c->vcur].p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0,
-           c->vel[1 - c->vcur].p, ghost_out(c, GA_VEL0 + (1 - c->vcur)));
+           c->vel[1 - c->vcur].p, ghost_out(c, GA_VEL0 + (1 - c->vcur)), 2);
+    (*c->cap_counter)--;
+  } else if (nonpressure_done)
+    LAUNCH(c, k_apply_accel, g, 128, c->dSt.p, c->acc.p, c->vel[c->vcur].p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0,
+           c->vel[1 - c->vcur].p, ghost_out(c, GA_VEL0 + (1 - c->vcur)), 0);
   else
     PLAUNCH(c, k_nonpressure, g, c->P, c->dSt.p, c->xrho.p, c->vel[c->vcur].p, c->bpos.p, c->bvel.p, list_f(c), list_b(c),
            c->normal.p, c->pstate[a].p, c->kappav[a].p, scale_kv ? 1 : 0, c->acc.p, c->vel[1 - c->vcur].p,
-           ghost_out(c, GA_VEL0 + (1 - c->vcur)));
+           ghost_out(c, GA_VEL0 + (1 - c->vcur)), 0);
   c->vcur = 1 - c->vcur;
   if (!c->slab.p2p) SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));  // peer stores: ordered by the CFL all-reduce below
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
@@ -1090,10 +1294,11 @@ int launch_step(dfr_context *c) {
                c->n_static_p, grid_static(c), grid_dyn(c), c->n_static_p > 0 ? 1 : 0, c->c_vol0.p, c->c_dens0.p, c->c_vel.p, c->c_dens.p,
                c->c_records.p);
         if (c->profiling) prof_begin(c, "k_contact_apply");
-        k_contact_apply<<<c->P.n_bodies, 32, (1 + c->P.n_bodies) * CG_N * sizeof(double), c->stream>>>(
+        k_contact_apply<<<c->P.n_bodies, 32, (1 + c->P.n_bodies) * CG_N * sizeof(double), c->ls>>>(
             c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, c->bpos.p, c->dyn_begin, c->c_order.p, c->c_records.p);
         if (c->profiling) prof_end(c);
-        c->launches++;
+        if (c->capturing) (*c->cap_counter)++;
+        else c->launches++;
       }
       LAUNCH(c, k_body_update, 1, 32, c->P, c->dSt.p, c->dBodies.p, c->dMgr.p, (int)BODY_POST);
     } else {
@@ -1168,6 +1373,8 @@ int reset_device_state(dfr_context *c) {
   st.nf = (int)c->nf_loc0;
   st.own_begin = 0;
   st.own_end = st.nf;
+  st.spec_div = 1;
+  st.div_streak = 2;
   if (c->slab.on) {
     c->slab.h_ranges[0] = 0;
     c->slab.h_ranges[1] = c->slab.h_ranges[2] = c->slab.h_ranges[3] = c->slab.h_ranges[4] = st.nf;
@@ -1292,6 +1499,7 @@ int dfr_create(const dfr_config *cfg, int device, dfr_context **out) {
     return DFR_ERR_CUDA;
   }
   std::memset(c->hSt, 0, sizeof(StepState));
+  c->ls = c->stream;
   *out = c;
   return DFR_OK;
 }
@@ -1300,6 +1508,9 @@ void dfr_destroy(dfr_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  drop_step_graphs(c);
+  for (auto &cs : c->cap_stream)
+    if (cs) cudaStreamDestroy(cs);
   for (int k = 0; k < 2; k++) {
     c->pos[k].free(); c->vel[k].free(); c->kappa[k].free(); c->kappav[k].free(); c->pid[k].free(); c->pstate[k].free();
   }
@@ -1878,8 +2089,99 @@ int dfr_set_gradient_mode(dfr_context *c, int mode) {
   if (mode < 0 || mode > 2) return fail(c, DFR_ERR_INVALID, "gradient mode must be 0 (Complete), 1 (Incomplete) or 2 (RigidGradOnly)");
   c->cfg.gradient_mode = mode;
   c->P.gradient_mode = mode;  // Params travel by value with every launch (__grid_constant__)
+  drop_step_graphs(c);        // ... and were recorded into the step graphs
   return DFR_OK;
 }
+
+namespace {
+// Enqueues n steps: recorded graphs where possible, the stream path otherwise.  gated = 1: steps after the end of the
+// trajectory are skipped on the device (the first step is never skipped).  hSt must be current on entry (every public
+// entry point that steps ends with a state read-back).
+struct StepBatch {
+  int64_t graph_steps = 0;
+  const dfr_context::StepGraph *last = nullptr;
+  long long it0 = 0, itv0 = 0;  // iteration totals when the first graph step of the batch was enqueued
+};
+// Graph stepping cannot look at the lists between the build and their first use, so it keeps the capacities at more
+// than twice the longest row seen (a row does not double within one CFL-limited step; an overflow still surfaces as
+// DFR_ERR_CAPACITY at the next read-back).  Unused ELL slots cost address space, not bandwidth.  The lists are rebuilt
+// from scratch every step, so re-allocating between two steps loses nothing.
+int relax_list_capacity(dfr_context *c) {
+  const bool f = 2 * (int)c->hSt->list_used_f > c->cap_f, b = 2 * (int)c->hSt->list_used_b > c->cap_b;
+  const bool d = 2ull * c->hSt->list_used_d > c->cap_d;
+  if (!f && !b && !d) return DFR_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  const size_t nwarp = ((size_t)c->nf_cap + 31) / 32;
+  if (f) {
+    const int want = ((int)(2 * c->hSt->list_used_f) + 8 + 3) & ~3;
+    if (want > 4096) return DFR_OK;  // stay on the watched stream path
+    c->idx_f.free();
+    CU(c->idx_f.alloc(nwarp * 32 * (size_t)want));
+    c->cap_f = want;
+  }
+  if (b) {
+    const int want = ((int)(2 * c->hSt->list_used_b) + 8 + 3) & ~3;
+    if (want > 4096) return DFR_OK;
+    c->idx_b.free();
+    CU(c->idx_b.alloc(nwarp * 32 * (size_t)want));
+    c->cap_b = want;
+  }
+  if (d) {
+    const unsigned long long want = 2ull * c->hSt->list_used_d + 1024;
+    if (want > (1ull << 31)) return DFR_OK;
+    c->idx_d.free();
+    CU(c->idx_d.alloc((size_t)want));
+    c->cap_d = (unsigned int)want;
+  }
+  drop_step_graphs(c);  // the list pointers and capacities are recorded in the graphs
+  return DFR_OK;
+}
+int enqueue_steps(dfr_context *c, int n_steps, int gated, StepBatch &B) {
+  for (int s = 0; s < n_steps; s++) {
+    if (graph_stepping_possible(c) && c->fresh_steps == 0) {
+      int rc = relax_list_capacity(c);
+      if (rc) return rc;
+    }
+    const bool risky = c->fresh_steps > 0 || 2 * (int)c->hSt->list_used_f > c->cap_f || 2 * (int)c->hSt->list_used_b > c->cap_b ||
+                       2ull * c->hSt->list_used_d > c->cap_d;
+    if (!graph_stepping_possible(c) || risky) {
+      const int cap_f = c->cap_f, cap_b = c->cap_b;
+      const unsigned int cap_d = c->cap_d;
+      int rc = launch_step(c);  // ends its solves with a read-back: hSt is current again
+      if (rc) return rc;
+      if (cap_f != c->cap_f || cap_b != c->cap_b || cap_d != c->cap_d) drop_step_graphs(c);  // lists were re-allocated
+      continue;
+    }
+    const int g = (gated && s > 0) ? 1 : 0;
+    dfr_context::StepGraph &sg = c->step_graph[g][c->cur];
+    if (!sg.exec) {
+      int rc = capture_step_graph(c, g);
+      if (rc) {  // keep working without graphs (the error text stays in last_error until the next failure)
+        c->graph_broken = 1;
+        s--;
+        continue;
+      }
+    }
+    int rc = contact_sort_tick(c);
+    if (rc) return rc;
+    if (B.graph_steps == 0) {
+      B.it0 = c->hSt->total_iters;
+      B.itv0 = c->hSt->total_iters_v;
+    }
+    CU(cudaGraphLaunch(sg.exec, c->stream));
+    c->cur = 1 - c->cur;  // the re-sort of the step flipped the buffers (vel flips twice per step)
+    B.graph_steps++;
+    B.last = &sg;
+  }
+  return DFR_OK;
+}
+// after the read-back that follows a batch: kernels the replayed steps launched
+void account_graph_launches(dfr_context *c, const StepBatch &B, int64_t steps_executed) {
+  if (!B.last) return;
+  c->launches += steps_executed * B.last->n_static + (c->hSt->total_iters_v - B.itv0) * B.last->n_div_body +
+                 (c->hSt->total_iters - B.it0) * B.last->n_prs_body;
+}
+}  // namespace
 
 int dfr_step(dfr_context *c, int n_steps) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
@@ -1890,15 +2192,17 @@ int dfr_step(dfr_context *c, int n_steps) {
     if (rc) return rc;
   }
   CU(cudaEventRecord(c->ev0, c->stream));
-  for (int s = 0; s < n_steps; s++) {
-    int rc = launch_step(c);
+  StepBatch B;
+  {
+    int rc = enqueue_steps(c, n_steps, 0, B);
     if (rc) return rc;
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   if (!c->bodies.empty())
     CU(cudaMemcpyAsync(c->h_bodies, c->dBodies.p, c->bodies.size() * sizeof(BodyDev), cudaMemcpyDeviceToHost, c->stream));
-  int rc = sync_state(c);
+  int rc = sync_state(c);  // the only synchronisation of a replayed dfr_step: status + the mirror the getters read
   if (rc) return rc;
+  account_graph_launches(c, B, B.graph_steps);
   c->bodies_mirrored = !c->bodies.empty();
   if (c->profiling) prof_resolve(c, c->hSt->div_iters, c->hSt->prs_iters);
   CU(cudaGetLastError());
@@ -1918,13 +2222,25 @@ int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
   }
   CU(cudaEventRecord(c->ev0, c->stream));
   int s = 0;
+  // batches of steps between two looks at `finished`; replayed steps past the end of the trajectory are skipped on the
+  // device (IF node), steps on the stream path are enqueued one at a time as before
+  const int batch_max = (graph_stepping_possible(c) && getenv_int("DFR_TRAJECTORY_BATCH") >= 0)
+                            ? std::max(1, getenv_int("DFR_TRAJECTORY_BATCH") ? getenv_int("DFR_TRAJECTORY_BATCH") : 16)
+                            : 1;
   while (s < max_steps) {
-    int rc = launch_step(c);
+    const bool risky = c->fresh_steps > 0;
+    const int nb = risky ? 1 : std::min(batch_max, max_steps - s);
+    const int count0 = c->hSt->step_count, cur0 = c->cur;
+    StepBatch B;
+    int rc = enqueue_steps(c, nb, 1, B);
     if (rc) return rc;
-    s++;
     rc = sync_state(c);
     if (rc) return rc;
-    if (c->hSt->finished) break;
+    const int done = c->hSt->step_count - count0;
+    account_graph_launches(c, B, std::max(0, done - (nb - (int)B.graph_steps)));
+    if (B.graph_steps) c->cur = cur0 ^ (done & 1);  // skipped steps did not flip the buffers
+    s += done;
+    if (c->hSt->finished || done < nb) break;
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaStreamSynchronize(c->stream));

@@ -810,6 +810,7 @@ struct RhoExtra {
   double *density, *factor;
   double4 *sgp, *xrho, *normal, *acc;
   GhostOut go;  // ghost rows of the extra gathered array (xrho or normal)
+  int gate;     // graph stepping: 0 always run, 1 run only if st->fuse_now, 2 run only if !st->fuse_now
 };
 // pair terms of SurfaceTension_Akinci2013::step (SurfaceTension_Akinci2013.cpp:60-151) and Viscosity_Standard::step
 // (Viscosity_Standard.cpp:233-334) for one fluid neighbour; r = x_i - x_j, c the cubic gradient coefficient
@@ -833,6 +834,9 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
   vsched_prologue(S);
   if (MODE == RHO_ITER) {
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+    // graph stepping launches the plain and the fused variant of every divergence iteration; one of them runs
+    if (X.gate == 1 && !st->fuse_now) return;
+    if (X.gate == 2 && st->fuse_now) return;
   }
   const int nf = st->nf;
   DFR_VB_LOOP(S) {
@@ -978,10 +982,18 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
 // Slab-decomposed contexts only store the local sum: the rule needs the sum over all slabs (k_solver_decide).
 #define RES_THREADS 256
 #define RES_BLOCKS 16
+// cond / policy (graph stepping, else 0): `cond` is the handle of the WHILE node this kernel's iteration body hangs in -
+// it is cleared when the solve closes; policy 1 = this is the divergence solve with the fused non-pressure pass enabled:
+// decide whether the next iteration carries it (the iteration count of the previous step predicts the last iteration;
+// once the prediction is exceeded every further iteration probably is the last) and whether the pass that just ran was
+// the last one (np_done).
 template <bool PRESSURE>
 __global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_constant__ Params P, StepState *st, const double *partials,
-                                                                 double *slice_sums) {
-  if (!(PRESSURE ? st->prs_active : st->div_active)) return;
+                                                                 double *slice_sums, unsigned long long cond, int policy) {
+  if (!(PRESSURE ? st->prs_active : st->div_active)) {
+    if (cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0u);
+    return;
+  }
   const int nf = st->nf;
   const int np = ((nf + 127) / 128) * 4;
   const int per = (np + RES_BLOCKS - 1) / RES_BLOCKS;
@@ -1027,14 +1039,32 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_co
     const int it = st->prs_iters + 1;
     st->prs_iters = it;
     const bool chk = (avg <= eta);
-    if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
+    const bool go_on = (!chk || it < P.min_iter) && it < P.max_iter;
+    if (!go_on) st->prs_active = 0;
+    if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, go_on ? 1u : 0u);
   } else {
     const double eta = (1.0 / st->h_step) * P.max_error_v * 0.01 * P.density0;
     const int it = st->div_iters + 1;
     st->div_iters = it;
     const bool chk = (avg <= eta);
-    if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
+    const bool go_on = (!chk || it < 1) && it < P.max_iter_v;
+    if (!go_on) st->div_active = 0;
+    if (policy == 1) {
+      if (go_on)
+        st->fuse_now = ((it + 1 == st->spec_div && st->div_streak >= 2) || it + 1 > st->spec_div) ? 1 : 0;
+      else {
+        st->np_done = st->fuse_now;  // the pass of this (last) iteration carried the non-pressure accelerations
+        st->div_streak = (it == st->spec_div) ? min(st->div_streak + 1, 1000) : 0;
+        st->spec_div = max(it, 1);
+      }
+    }
+    if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, go_on ? 1u : 0u);
   }
+}
+// graph stepping: opens the IF node that holds a whole step unless the trajectory has finished (dfr_run_trajectory
+// enqueues steps in batches and looks at the state once per batch)
+__global__ void k_step_gate(const StepState *st, unsigned long long cond, int respect_finished) {
+  cudaGraphSetConditional((cudaGraphConditionalHandle)cond, (respect_finished && st->finished) ? 0u : 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1320,8 +1350,9 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
 __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
                                                       const double4 *bvel, NbrList lf, NbrList lb,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
-                                                      double4 *acc_out, double4 *vel_out, const GhostOut GO, const VSched S) {
+                                                      double4 *acc_out, double4 *vel_out, const GhostOut GO, int gate, const VSched S) {
   vsched_prologue(S);
+  if (gate == 1 && st->np_done) return;  // graph stepping: the fused pass of the last divergence iteration did this work
   const int nf = st->nf;
   const double h = st->h_step;
   DFR_VB_LOOP(S) {
@@ -1403,7 +1434,8 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
 // v += h a, CFL maximum and kappa_v rescale for accelerations that a fused k_rho pass wrote (RHO_X_NONPRESSURE):
 // the tail of k_nonpressure as a streaming pass (TimeStepDiffDFSPH.cpp:589-604, Simulation.cpp:542-575)
 __global__ void __launch_bounds__(128) k_apply_accel(StepState *st, const double4 *acc, const double4 *vel, const int *state, double *kappav,
-                                                      int scale_kappav, double4 *vel_out, const GhostOut GO) {
+                                                      int scale_kappav, double4 *vel_out, const GhostOut GO, int gate) {
+  if (gate == 2 && !st->np_done) return;  // graph stepping: k_nonpressure ran instead
   const double h = st->h_step;
   const int i = blockIdx.x * 128 + threadIdx.x;
   double mag = 0.0;

@@ -64,6 +64,11 @@ struct StepState {
   double last_residual;
   double res_sum;                   // slab mode: local residual sum of the iteration, all-reduced before the stopping rule
   int slab_ranges[8];               // slab mode: own_begin, own_end, end of the low boundary layer, begin of the high one, nf
+  // CUDA-graph stepping (dfr_api.cu: StepGraph): the solver loops are WHILE nodes, so what the host used to decide
+  // between speculated batches is decided here
+  int spec_div, div_streak;         // divergence iterations of the previous step / consecutive steps that matched the prediction
+  int fuse_now;                     // the next divergence iteration's k_rho also evaluates the non-pressure accelerations
+  int np_done;                      // ... and that pass was the last active iteration: k_apply_accel instead of k_nonpressure
 };
 
 // Accumulator row written by the boundary-side kernel, per block: the eight net Jacobian blocks of
