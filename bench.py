@@ -12,7 +12,8 @@ per GPU) there are two shardings, `--mode`:
   slab      (default) ONE scene of N x 2^20 particles, slab-decomposed over the N GPUs: boundary-layer particles, ghost
             updates of every gathered array, residuals, the CFL maximum and the rigid force/torque/Jacobian rows travel
             over NVLink (NCCL) inside every step (BASELINE.json configs[4])
-  rollouts  N independent rollouts of the 2^20-particle scene (population sharding, configs[3]); no data-path collective
+  rollouts  a population of 64 independent rollouts at the high-diving scene's size, sharded over the N GPUs with several
+            contexts side by side per GPU (population sharding, configs[3]); no data-path collective; also valid at N = 1
 """
 from __future__ import annotations
 
@@ -311,6 +312,87 @@ def pysplishsplash_leg(scene, steps, device):
                     "velocities and the eight sensitivity blocks of every dynamic body as numpy arrays"}
 
 
+def rollouts_mode(args, rank, world, local_rank, dist, torch):
+    """BASELINE.json configs[3]: a CMA-ES-sized population of independent rollouts sharded over the GPUs.
+
+    64 candidate (v0, omega0) pairs drawn with numpy.random.default_rng(12) (opt-ng.py: seed 12; the reference evaluates
+    its nevergrad population one candidate after the other) on a scene of the high-diving configuration's size (118,389
+    fluid particles; synthetic dam break + one dynamic box, fixed time step, `--rollout-steps` steps per trajectory).
+    Each rank evaluates its block with `--concurrency` contexts side by side on its GPU; no data-path collective, one
+    small all_gather of the results.  Timed with the wall clock between device synchronisations (several streams per
+    GPU), maximum over ranks."""
+    from difffr_b200 import rollouts, scenes
+    from difffr_b200.cabi import Context
+
+    n_cand, n_part, steps = args.candidates, args.rollout_particles, args.rollout_steps
+    scene = scenes.dam_break_scene(n_part, n_boxes=1)
+    cfg = dict(CFG)
+    cfg.update(cfl_method=0, time_step_size=1.0e-3, uniform_acc_rb_time=0.02, target_time=steps * 1.0e-3 - 0.02 - 0.5e-3)
+    rng = np.random.default_rng(12)
+    cands = [(rng.normal(size=3), rng.normal(size=3)) for _ in range(n_cand)]
+    body = [i for i, b in enumerate(scene["bodies"]) if b["dynamic"]][0]
+
+    def make():
+        return scenes.build_context(lambda **k: Context(device=local_rank, **k), scene, **cfg)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gather = rollouts.torch_gather(world) if dist is not None else None
+    conc = max(1, args.concurrency)
+    ctxs = [make() for _ in range(conc)]
+    nf = ctxs[0].num_fluid
+    # warm-up: one rollout per context (graph capture, capacity checks)
+    rollouts.run_population(None, cands[:conc * world], body, rank, world, max_steps=steps + 10, gather=gather, contexts=ctxs)
+    results = {}
+    legs = [("concurrent", ctxs)] + ([("serial", ctxs[:1])] if world == 1 and conc > 1 and not args.no_serial_leg else [])
+    for label, cs in legs:
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and label == "concurrent":
+            sampler.start()
+        stats = {}
+        t0 = time.perf_counter()
+        res, nsteps = rollouts.run_population(None, cands, body, rank, world, max_steps=steps + 10, gather=gather, contexts=cs, stats=stats)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if (rank == 0 and label == "concurrent") else None
+        launches = stats.get("kernel_launches", 0)
+        if dist is not None:
+            t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+            w = torch.tensor([launches], dtype=torch.float64, device="cuda")
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+            launches = float(w.item())
+        results[label] = dict(wall=wall, steps=int(nsteps.sum()), launches=launches, clocks=clocks, checksum=float(np.abs(res).sum()))
+    if rank != 0:
+        return
+    c = results["concurrent"]
+    value = nf * c["steps"] / c["wall"]
+    line = {
+        "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * c["wall"] / max(c["steps"], 1) * world * conc, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"population of {n_cand} independent rollouts (BASELINE.json configs[3]: CMA-ES-sized population, candidates from "
+                               f"numpy default_rng(12)); synthetic dam break + 1 dynamic box at the high-diving scene's size ({nf} fluid particles), "
+                               f"{steps} steps per trajectory, fixed h = 1e-3; forward step + Jacobians + sensitivity chain rule",
+                   "particles_per_rollout": nf, "rollouts": n_cand, "steps_per_rollout": steps,
+                   "parallelism": f"candidates sharded over {world} GPU(s), {conc} contexts side by side per GPU; no data-path collective",
+                   "l2": "several independent working sets per GPU, each larger than its share of the 126 MB L2; no flush needed"},
+        "rollouts_per_s": n_cand / c["wall"], "seconds_per_population": c["wall"], "concurrency": conc,
+        "clocks": c["clocks"], "gpu_launches": int(c["launches"]),
+        "timing": "wall clock between device synchronisations (several streams per GPU), max over ranks",
+    }
+    if "serial" in results:
+        sr = results["serial"]
+        line["serial"] = {"seconds_per_population": sr["wall"], "value": nf * sr["steps"] / sr["wall"],
+                          "speedup_of_concurrent": sr["wall"] / c["wall"], "same_results": sr["checksum"] == c["checksum"]}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -326,6 +408,11 @@ def main():
     ap.add_argument("--no-settled-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-pysph-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--preroll", type=int, default=1200, help=argparse.SUPPRESS)
+    ap.add_argument("--candidates", type=int, default=64, help="--mode rollouts: population size")
+    ap.add_argument("--concurrency", type=int, default=4, help="--mode rollouts: contexts side by side per GPU")
+    ap.add_argument("--rollout-particles", type=int, default=118389, help=argparse.SUPPRESS)
+    ap.add_argument("--rollout-steps", type=int, default=200, help=argparse.SUPPRESS)
+    ap.add_argument("--no-serial-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -351,6 +438,12 @@ def main():
 
     from difffr_b200 import scenes
     from difffr_b200.cabi import Context
+
+    if args.mode == "rollouts":
+        rollouts_mode(args, rank, world, local_rank, dist, torch)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     slab = world > 1 and args.mode == "slab"
     n_particles = args.particles * (world if slab else 1)

@@ -133,6 +133,7 @@ struct dfr_context {
   // grids
   DevBuf<unsigned int> cell_start_f, cell_start_s, cell_start_d, tile_sums;
   DevBuf<unsigned char> near_s;  // per cell: a static boundary particle may be within reach (k_mark_near, marked once)
+  DevBuf<unsigned char> near_d;  // the same for the dynamic boundary particles, re-marked with their cell table
   DevBuf<int> cell_of_p, rank_in_cell, sorted_src_f, sorted_src_d, cell_of_b, rank_b;
   // neighbour lists
   DevBuf<int> cnt_f, cnt_b, idx_f, idx_b, idx_d;
@@ -307,7 +308,7 @@ int persistent_grid(dfr_context *c, K kernel, int nvb) {
     if ((nvb) > 0) {                                                                          \
       const int pg__ = persistent_grid((c), kernel, (nvb));                                   \
       if ((c)->profiling) prof_begin((c), #kernel);                                           \
-      kernel<<<pg__, 128, 0, (c)->ls>>>(__VA_ARGS__, next_sched((c), (nvb)));                 \
+      kernel<<<(pg__ + DFR_CTA_VB - 1) / DFR_CTA_VB, DFR_CTA_THREADS, 0, (c)->ls>>>(__VA_ARGS__, next_sched((c), (nvb))); \
       if ((c)->profiling) prof_end((c));                                                      \
       if ((c)->capturing) (*(c)->cap_counter)++;                                              \
       else (c)->launches++;                                                                   \
@@ -415,6 +416,10 @@ int build_dyn_grid(dfr_context *c) {
          c->rank_b.p, c->sorted_src_d.p);
   LAUNCH(c, k_bin_sort_cells_by_particle, cdiv(c->n_dyn_p, 128), 128, (const int *)nullptr, c->n_dyn_p, c->cell_start_d.p,
          c->cell_of_b.p, c->rank_b.p, c->sorted_src_d.p);
+  // cells from which a dynamic boundary particle may be within reach: the list build skips the 25-row walk over this
+  // set for every fluid particle elsewhere (most of the fluid)
+  cudaMemsetAsync(c->near_d.p, 0, (size_t)nc, c->ls);
+  LAUNCH(c, k_mark_near_warp, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p + c->dyn_begin, c->n_dyn_p, c->near_d.p);
   return DFR_OK;
 }
 
@@ -453,7 +458,7 @@ int build_neighbor_lists(dfr_context *c) {
   if (rc) return rc;
   PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
          c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
-         c->near_s.p);
+         c->near_s.p, c->near_d.p);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->ls);
     LAUNCH(c, k_dnbr_count, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
@@ -1520,6 +1525,7 @@ void dfr_destroy(dfr_context *c) {
   c->bbody_tmp.free(); c->borig_tmp.free(); c->bvol.free(); c->dBodies.free(); c->dMgr.free(); c->acc_rows.free();
   c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
   c->near_s.free();
+  c->near_d.free();
   c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
@@ -1911,6 +1917,7 @@ int dfr_finalize(dfr_context *c) {
   if (cudaMallocHost((void **)&c->h_init, std::max<size_t>(c->bodies.size(), 1) * 6 * sizeof(double)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   CU(c->cell_start_f.alloc((size_t)nc + 1)); CU(c->cell_start_s.alloc((size_t)nc + 1)); CU(c->cell_start_d.alloc((size_t)nc + 1));
   CU(c->near_s.alloc((size_t)nc));
+  CU(c->near_d.alloc((size_t)nc));
   CU(cudaMemsetAsync(c->near_s.p, 0, (size_t)nc, c->stream));
   const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));

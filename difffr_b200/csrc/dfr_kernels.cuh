@@ -60,6 +60,21 @@ struct Rec3 {
 #ifndef DFR_SM_LOCAL
 #define DFR_SM_LOCAL 0
 #endif
+// Virtual 128-particle blocks per CTA of the list kernels: a CTA of 128 * DFR_CTA_VB threads works on that many
+// CONSECUTIVE virtual blocks, i.e. on one contiguous run of cell-sorted particles whose neighbourhoods overlap, so that
+// the warps sharing an SM's L1 at any time gather from the same few hundred KB instead of from 8 unrelated strips
+// (tools/gather_locality.py: the gathers of 128 consecutive particles can hit L1 at most 70 % of the time on the bench
+// scene's 93-cell rows, those of 1024 consecutive particles 85 %).  Indexing inside a virtual block is unchanged, so every
+// sum has the same order for every DFR_CTA_VB.
+#ifndef DFR_CTA_VB
+#define DFR_CTA_VB 1
+#endif
+#if DFR_SM_LOCAL && DFR_CTA_VB != 1
+#error "DFR_SM_LOCAL and DFR_CTA_VB are alternatives"
+#endif
+#define DFR_CTA_THREADS (128 * DFR_CTA_VB)
+#define DFR_TID (threadIdx.x & 127)
+#define DFR_RESIDENT(blocks) ((blocks) / DFR_CTA_VB > 0 ? (blocks) / DFR_CTA_VB : 1)
 #define DFR_SCHED_STRIDE 256
 struct VSched {
   unsigned int *ctr;  // [2][DFR_SCHED_STRIDE]
@@ -107,7 +122,7 @@ __device__ __forceinline__ int vsched_next(const VSched &S, VState &v, int *sh) 
   VState vb_state_ = vsched_begin(S); \
   for (int vb_ = vsched_next(S, vb_state_, &vb_sh_); vb_ >= 0; vb_ = vsched_next(S, vb_state_, &vb_sh_))
 #else
-#define DFR_VB_LOOP(S) for (int vb_ = blockIdx.x, once_ = 1; once_; once_ = 0)
+#define DFR_VB_LOOP(S) for (int vb_ = blockIdx.x * DFR_CTA_VB + (threadIdx.x >> 7), once_ = 1; once_; once_ = 0)
 #endif
 
 // read-only 32-byte record load as ONE 256-bit instruction (sm_100: LDG.E.ENL2.256.CONSTANT).  A gathered
@@ -547,8 +562,20 @@ __global__ void k_permute_boundary(int n, const int *sorted_src, const double4 *
 // "A point of this set may be within reach": one byte per cell, set for every cell of the (2 reach + 1)^3 block around
 // the cell of each point - exactly the cells whose stencil walk (for_each_in_range) would visit that point's cell.
 // The list build reads the byte of a fluid particle's own cell and skips the whole 25-row walk over the static
-// boundary set when it is 0 (true for most of the fluid).  Marked once: static particles never move.  (Marking the
-// dynamic set every step as well was measured: it costs small scenes more than it saves.)
+// boundary set when it is 0 (true for most of the fluid).  Marked once for the static set (those particles never move)
+// and with every rebuild of the dynamic set's cell table (k_mark_near_warp: few particles, so one warp per particle).
+__global__ void k_mark_near_warp(const __grid_constant__ Params P, const double4 *pos, int n, unsigned char *near_flag) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= n) return;
+  const double4 p = pos[t];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int R = P.grid.reach, W = 2 * R + 1;
+  for (int k = lane; k < W * W * W; k += 32) {
+    const int x = cx - R + k % W, y = cy - R + (k / W) % W, z = cz - R + k / (W * W);
+    if (x >= 0 && x < P.grid.nx && y >= 0 && y < P.grid.ny && z >= 0 && z < P.grid.nz) near_flag[cell_lin(P.grid, x, y, z)] = 1;
+  }
+}
 __global__ void k_mark_near(const __grid_constant__ Params P, const double4 *pos, int n, unsigned char *near_flag) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -594,14 +621,14 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
 // Single scan: fluid->fluid and fluid->boundary neighbour lists in a warp-interleaved ELL layout
 // (dfr_types.cuh: "ELL-4"; no count pass / prefix sum is needed).  Rows longer than cap raise error_flags and report
 // their length; the host then grows the capacity and rebuilds the lists (dfr_api.cu: ensure_list_capacity).
-__global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
+__global__ void __launch_bounds__(DFR_CTA_THREADS) k_nbr_build(const __grid_constant__ Params P, StepState *st, const double4 *pos, GridView gf,
                                                     GridView gs, GridView gd, int has_static, int has_dyn, int *cnt_f, int *cnt_b,
                                                     int *idx_f, int *idx_b, int cap_f, int cap_b, const unsigned char *near_s,
-                                                    const VSched S) {
+                                                    const unsigned char *near_d, const VSched S) {
   vsched_prologue(S);
   const int n = st->nf;
   DFR_VB_LOOP(S) {
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   int cf = 0, cb = 0;
   (void)n;
   if (i >= st->own_begin && i < st->own_end) {
@@ -619,7 +646,7 @@ __global__ void __launch_bounds__(128) k_nbr_build(const __grid_constant__ Param
       if (cb < cap_b) idx_b[nbr_slot(cap_b, i, cb)] = j;
       cb++;
     });
-    if (has_dyn) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int j) {
+    if (has_dyn && near_d[own_cell]) for_each_in_range(P, gd, p.x, p.y, p.z, -1, [&](int j) {
       if (cb < cap_b) idx_b[nbr_slot(cap_b, i, cb)] = j;
       cb++;
     });
@@ -747,12 +774,12 @@ __global__ void k_store_volume(double4 *bpos, const double *vol, int n_b) {
 // density + DFSPH factor, fused (TimeStep::computeDensities, TimeStep.cpp:147-200;
 // computeDFSPHFactor, TimeStepDiffDFSPH.cpp:883-962)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_density_factor(const __grid_constant__ Params P, const StepState *st, const double4 *pos, const double4 *bpos,
+__global__ void __launch_bounds__(DFR_CTA_THREADS) k_density_factor(const __grid_constant__ Params P, const StepState *st, const double4 *pos, const double4 *bpos,
                                                          NbrList lf, NbrList lb, double *density, double *factor, double4 *sgp, double4 *xrho,
                                                          const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   if (i < st->own_begin || i >= st->own_end) continue;
   const double4 pi = pos[i];
   double dens = P.volume * P.W_zero;
@@ -827,7 +854,7 @@ __device__ __forceinline__ void nonpressure_pair(const Params &P, bool st_on, bo
 }
 
 template <bool PRESSURE, int MODE, int EXTRA = RHO_X_NONE>
-__global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (EXTRA == RHO_X_NONPRESSURE ? DFR_RHONP_BLOCKS : DFR_RHOX_BLOCKS))) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(DFR_CTA_THREADS, DFR_RESIDENT(EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (EXTRA == RHO_X_NONPRESSURE ? DFR_RHONP_BLOCKS : DFR_RHOX_BLOCKS))) k_rho(const __grid_constant__ Params P, StepState *st, const double4 *pos, const double4 *vel, const double4 *bpos,
                                               const double4 *bvel, NbrList lf, NbrList lb, const double *density, const double *factor,
                                               const int *state, double *kappa, double *dadv, double4 *xk, double *partials, const GhostOut GO,
                                               const RhoExtra X, const VSched S) {
@@ -841,7 +868,7 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
   const int nf = st->nf;
   DFR_VB_LOOP(S) {
   if (vb_ * 128 >= nf) continue;  // grids are sized for the emitter capacity; only live blocks take a ticket
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   const double h = PRESSURE ? st->h : st->h_step;
   double err = 0.0;
   if (i >= st->own_begin && i < st->own_end) {
@@ -970,7 +997,7 @@ __global__ void __launch_bounds__(128, (EXTRA == RHO_X_NONE ? DFR_RHO_BLOCKS : (
     double s = err;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(DFR_FULL, s, o);
-    if ((threadIdx.x & 31) == 0) partials[(size_t)vb_ * 4 + (threadIdx.x >> 5)] = s;
+    if ((threadIdx.x & 31) == 0) partials[(size_t)vb_ * 4 + (DFR_TID >> 5)] = s;
   }
   }
 }
@@ -1073,7 +1100,7 @@ __global__ void k_step_gate(const StepState *st, unsigned long long cond, int re
 // (k_boundary_side) instead of being scattered from here.
 // ---------------------------------------------------------------------------------------------
 template <bool PRESSURE, bool ITER>
-__global__ void __launch_bounds__(128, DFR_PUSH_BLOCKS) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(DFR_CTA_THREADS, DFR_RESIDENT(DFR_PUSH_BLOCKS)) k_push(const __grid_constant__ Params P, const StepState *st, const double4 *xk, double4 *vel, const double4 *bpos,
                                                NbrList lf, NbrList lb, const int *state, double *kappa, int accumulate_kappa,
                                                const GhostOut GO, const VSched S) {
   vsched_prologue(S);
@@ -1081,7 +1108,7 @@ __global__ void __launch_bounds__(128, DFR_PUSH_BLOCKS) k_push(const __grid_cons
     if (!(PRESSURE ? st->prs_active : st->div_active)) return;
   }
   DFR_VB_LOOP(S) {
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   if (i < st->own_begin || i >= st->own_end) continue;
   if (state[i] != 0) continue;
   const double h = PRESSURE ? st->h : st->h_step;
@@ -1326,11 +1353,11 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_co
 // clearAccelerations (TimeStep.cpp:66-81), v += h a (TimeStepDiffDFSPH.cpp:589-604) and the CFL
 // maximum (Simulation.cpp:542-575), fused.  kappa_v *= h_step of divergenceSolve (:870-880) rides along.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params P, const StepState *st, const double4 *xrho, NbrList lf,
+__global__ void __launch_bounds__(DFR_CTA_THREADS) k_normals(const __grid_constant__ Params P, const StepState *st, const double4 *xrho, NbrList lf,
                                                   double4 *normal, const GhostOut GO, const VSched S) {
   vsched_prologue(S);
   DFR_VB_LOOP(S) {
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   if (i < st->own_begin || i >= st->own_end) continue;
   const double4 pi = xrho[i];
   d3 n = mk3(0, 0, 0);
@@ -1347,7 +1374,7 @@ __global__ void __launch_bounds__(128) k_normals(const __grid_constant__ Params 
   }
 }
 
-__global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
+__global__ void __launch_bounds__(DFR_CTA_THREADS) k_nonpressure(const __grid_constant__ Params P, StepState *st, const double4 *xrho, const double4 *vel, const double4 *bpos,
                                                       const double4 *bvel, NbrList lf, NbrList lb,
                                                       const double4 *normal, const int *state, double *kappav, int scale_kappav,
                                                       double4 *acc_out, double4 *vel_out, const GhostOut GO, int gate, const VSched S) {
@@ -1356,7 +1383,7 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
   const int nf = st->nf;
   const double h = st->h_step;
   DFR_VB_LOOP(S) {
-  const int i = vb_ * 128 + threadIdx.x;
+  const int i = vb_ * 128 + DFR_TID;
   double mag = 0.0;
   (void)nf;
   if (i >= st->own_begin && i < st->own_end) {
@@ -1421,13 +1448,8 @@ __global__ void __launch_bounds__(128) k_nonpressure(const __grid_constant__ Par
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mag = fmax(mag, __shfl_xor_sync(DFR_FULL, mag, o));
-  __shared__ double wmax[4];
-  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double m = fmax(fmax(wmax[0], wmax[1]), fmax(wmax[2], wmax[3]));
-    atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(m));
-  }
+  // one atomic per warp (a maximum does not depend on the order; no barrier, so the kernel works for any DFR_CTA_VB)
+  if ((threadIdx.x & 31) == 0 && mag > 0.0) atomicMax(&st->cfl_max_bits, (unsigned long long)__double_as_longlong(mag));
   }
 }
 

@@ -54,24 +54,71 @@ def unpack_result(vec: np.ndarray):
 
 
 def run_population(make_context, candidates, body: int, rank: int = 0, world_size: int = 1, max_steps: int = 1 << 30,
-                   gather=None):
+                   gather=None, concurrency: int = 1, contexts=None, stats=None):
     """Evaluate `candidates` (sequence of (v0, omega0) pairs for rigid body `body`), sharded over ranks.
 
-    make_context() -> a finalized Context; one is created per rank and reset between rollouts
-    (dfr_reset is a device-to-device restore of the initial state held in HBM).
+    make_context() -> a finalized Context; `concurrency` of them are created per rank and reset between rollouts
+    (dfr_reset is a device-to-device restore of the initial state held in HBM).  Contexts are independent (own device
+    memory, own CUDA stream, no globals), so with concurrency > 1 the rank's candidates are evaluated by that many
+    host threads, each driving its own context: the kernels of a paper-scale scene (~10^5 particles) fill only part of a
+    B200, and rollouts running side by side on different streams fill the rest.  The result of a candidate does not
+    depend on which context ran it or on what ran beside it (deterministic kernels, no shared state).
+    `contexts`: reuse these finalized contexts instead of calling make_context (len(contexts) overrides concurrency).
     gather(local: np.ndarray[n_local, W]) -> np.ndarray[n_total, W] concatenates rank blocks in rank
     order; None means single process.  Returns (results [n, RESULT_WIDTH], steps [n]) on every rank.
+    stats: optional dict; "kernel_launches" is incremented by the kernels this rank's rollouts launched.
     """
     mine = shard_indices(len(candidates), rank, world_size)
     local = np.zeros((len(mine), RESULT_WIDTH + 1))
-    ctx = make_context() if mine else None
-    for k, ci in enumerate(mine):
-        v0, w0 = candidates[ci]
+    launches = np.zeros(len(mine), dtype=np.int64)
+    if contexts is not None:
+        concurrency = len(contexts)
+    concurrency = max(1, min(int(concurrency), max(len(mine), 1)))
+
+    def evaluate(ctx, k):
+        v0, w0 = candidates[mine[k]]
         ctx.set_init_v_omega(body, v0, w0)
         ctx.reset()
         steps = ctx.run_trajectory(max_steps)
         local[k, :RESULT_WIDTH] = pack_result(ctx, body)
         local[k, RESULT_WIDTH] = steps
+        launches[k] = ctx.device_time_ms()[1]  # counted since the reset that started this rollout
+
+    if mine:
+        ctxs = list(contexts[:concurrency]) if contexts is not None else [make_context() for _ in range(concurrency)]
+        if concurrency == 1:
+            for k in range(len(mine)):
+                evaluate(ctxs[0], k)
+        else:
+            import queue
+            import threading
+
+            work = queue.SimpleQueue()
+            for k in range(len(mine)):
+                work.put(k)
+            errors = []
+
+            def worker(ctx):
+                # the C-ABI calls release the GIL (ctypes), so the threads only serialise on the tiny Python parts
+                try:
+                    while True:
+                        try:
+                            k = work.get_nowait()
+                        except queue.Empty:
+                            return
+                        evaluate(ctx, k)
+                except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                    errors.append(e)
+
+            threads = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+    if stats is not None:
+        stats["kernel_launches"] = stats.get("kernel_launches", 0) + int(launches.sum())
     allr = gather(local) if gather is not None else local
     return allr[:, :RESULT_WIDTH], allr[:, RESULT_WIDTH].astype(np.int64)
 

@@ -164,11 +164,20 @@ int dfr_reset_gradient(dfr_context *ctx);
 int dfr_set_gradient_mode(dfr_context *ctx, int mode);
 
 /* n x SimulatorBase::timeStepNoGUI body (SimulatorBase.cpp:1142-1169): TimeStepDiffDFSPH::step,
- * gradient-manager stages, rigid velocity/position update.  No host round trip inside. */
+ * gradient-manager stages, rigid velocity/position update.
+ * Steady state (single context): every step is one replay of a recorded CUDA graph whose two Jacobi loops are
+ * conditional WHILE nodes - the stopping rules of TimeStepDiffDFSPH.cpp:711-743 / 828-861 run on the device - so there
+ * is no host round trip inside the n steps; the call ends with ONE synchronisation that brings back the status word and
+ * the body records the getters read.  The stream path (speculated batches of iterations, one read-back per solve) is
+ * used instead: in the first four steps after finalize / reset / load (the neighbour-list capacities are being
+ * watched), with the rigid contact solver once every 500 steps (the reference's z-sort of the contact order runs on the
+ * host), while per-kernel profiling is on, on slab-decomposed contexts, and with DFR_NO_GRAPH=1. */
 int dfr_step(dfr_context *ctx, int n_steps);
 
 /* Runs steps until TimeStepDiffDFSPH::is_trajectory_finish_callback() would be true
- * (TimeStepDiffDFSPH.cpp:448) or max_steps is hit; writes the number of steps taken. */
+ * (TimeStepDiffDFSPH.cpp:448) or max_steps is hit; writes the number of steps taken.
+ * Replayed steps are enqueued in batches of 16 (DFR_TRAJECTORY_BATCH) with one state read-back per batch; steps of a
+ * batch that follow the end of the trajectory are skipped on the device (an IF node around the step). */
 int dfr_run_trajectory(dfr_context *ctx, int max_steps, int *steps_done);
 
 /* Simulation time data: TimeManager::getTime/getTimeStepSize (TimeModule.cpp:23-29),

@@ -8,11 +8,11 @@ regenerated: the reference build runs the scene forward from the lattice with th
 the column has collapsed to its rest height, and the positions are kept as float32 (the precision of the reference's own
 .bgeo state files).  Both sides then start from that file with zero velocities (--load-fluid-pos semantics).
 
-  python tests/golden/make_trajectory_golden.py settle stone_skipping     -> tests/golden/stone_skipping_settled.npz
+  python tests/golden/make_trajectory_golden.py settle stone_skipping     -> tests/golden/trajectory/stone_skipping_settled.npz
       (CPU, reference build; slow: the column sloshes for seconds of simulated time.  The committed file was made on the
       GPU instead: `dump stone_skipping gpurun_in/stone.npz`, then tools/settle_scene.py under gpurun)
-  python tests/golden/make_trajectory_golden.py record stone_skipping     -> tests/golden/paper_stone_skipping.npz
-  python tests/golden/make_trajectory_golden.py record stone_skipping orc -> /tmp/paper_stone_skipping_orc.npz (the oracle
+  python tests/golden/make_trajectory_golden.py record stone_skipping     -> tests/golden/trajectory/traj_stone_skipping.npz
+  python tests/golden/make_trajectory_golden.py record stone_skipping orc -> /tmp/traj_stone_skipping_orc.npz (the oracle
       port on the same inputs: how far two FP-different CPU implementations drift over the trajectory)
 
 The record holds the complete inputs except the fluid positions (the settled file), per step the rigid state, time step
@@ -26,8 +26,9 @@ import time
 
 import numpy as np
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+GOLDEN = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(GOLDEN, "trajectory")  # kept apart from the per-step goldens, which the tests find by globbing *.npz
+ROOT = os.path.dirname(os.path.dirname(GOLDEN))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -141,7 +142,7 @@ def record(name, lib_kind="ref"):
     out["body_force_torque"] = np.array(fts)
     out["grad_steps"] = np.array(grad_steps)
     out["body_grads"] = np.array(grads)
-    path = os.path.join(HERE, f"paper_{name}.npz") if lib_kind == "ref" else f"/tmp/paper_{name}_{lib_kind}.npz"
+    path = os.path.join(HERE, f"traj_{name}.npz") if lib_kind == "ref" else f"/tmp/traj_{name}_{lib_kind}.npz"
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(states), "steps")
 

@@ -77,6 +77,26 @@ def test_scene_loader_rejects_what_is_outside_the_path(tmp_path):
         sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"boundaryHandlingMethod": 2}))
     with pytest.raises(RuntimeError):
         sph._load_scene_summary(str(tmp_path / "missing.json"))
+    # keys whose physics this path does not carry must not be ignored silently (the reference's cart-pole scene sets all
+    # of them: experiments/on_water_inverted_pendulum/scene/cartpole-diff-controller.json)
+    with pytest.raises(RuntimeError, match="sim2D"):
+        sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"sim2D": True}))
+    import json
+    for key, value, pattern in (("ArticulatedSystems", [{"rigidIndices": [1], "joints": []}], "ArticulatedSystems"),
+                                ("FluidModels", [{"particleFile": "x.bgeo"}], "FluidModels")):
+        path = write_scene(tmp_path)
+        sc = json.load(open(path))
+        sc[key] = value
+        json.dump(sc, open(path, "w"))
+        with pytest.raises(RuntimeError, match=pattern):
+            sph._load_scene_summary(path)
+    path = write_scene(tmp_path)
+    sc = json.load(open(path))
+    sc["RigidBodies"][1]["isAnimated"] = True
+    json.dump(sc, open(path, "w"))
+    with pytest.raises(RuntimeError, match="isAnimated"):
+        sph._load_scene_summary(path)
+    sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"sim2D": False}))  # the 3-D default spelled out is fine
 
 
 def test_no_cpu_fallback(tmp_path):
