@@ -1594,14 +1594,21 @@ __global__ void k_emit_spawn(const __grid_constant__ Params P, StepState *st, Em
   const double startX = -0.5 * (e.width - 1) * diam;
   const double startZ = -0.5 * (e.height - 1) * diam;
   const double dt = t - e.next_emit_time + st->h;
-  const d3 offset = e.x + dt * ev;
+  // every product and sum below is rounded on its own (no FMA contraction), in the reference's order (Emitter.cpp:171):
+  // a sheet is an exact 2r lattice with pairs at distance == support radius, and Akinci-2013's normal term is not
+  // kernel-weighted, so one differing bit in an emitted position can flip such a pair in or out of the lists and change
+  // the surface-tension force by O(1)
+  const d3 offset = mk3(__dadd_rn(e.x.x, __dmul_rn(dt, ev.x)), __dadd_rn(e.x.y, __dmul_rn(dt, ev.y)), __dadd_rn(e.x.z, __dmul_rn(dt, ev.z)));
   if (nf < capacity) {
     const int total = e.width * e.height;
     for (int k = threadIdx.x; k < total; k += blockDim.x) {
       const int i = k / e.height, j = k % e.height;
       const int index = nf + k;
       if (index < capacity) {
-        const d3 x = (i * diam + startX) * axisW + (j * diam + startZ) * axisH + offset;
+        const double sw = __dadd_rn(__dmul_rn((double)i, diam), startX), sh = __dadd_rn(__dmul_rn((double)j, diam), startZ);
+        const d3 x = mk3(__dadd_rn(__dadd_rn(__dmul_rn(sw, axisW.x), __dmul_rn(sh, axisH.x)), offset.x),
+                         __dadd_rn(__dadd_rn(__dmul_rn(sw, axisW.y), __dmul_rn(sh, axisH.y)), offset.y),
+                         __dadd_rn(__dadd_rn(__dmul_rn(sw, axisW.z), __dmul_rn(sh, axisH.z)), offset.z));
         pos[index] = make_double4(x.x, x.y, x.z, 0.0);
         vel[index] = make_double4(ev.x, ev.y, ev.z, 0.0);
         state[index] = 1;

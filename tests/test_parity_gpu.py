@@ -289,6 +289,27 @@ def test_emitter_grows_the_fluid(gpu_factory, oracle_factory):
     compare_step(gpu, orc, sc)
 
 
+def test_emitter_with_surface_tension(gpu_factory, oracle_factory):
+    """The same emitters with Akinci-2013 surface tension ON, as in diff-high-diving-duck.json (BASELINE.json configs[3]).
+    Emitted positions are computed with the reference's rounding (k_emit_spawn), so the sheets' pairs at distance ==
+    support radius fall on the same side of the strict `<` on both sides and the O(1) normal term agrees."""
+    sc = scenes.dam_break_scene(2000, n_boxes=1)
+    he = sc["tank_half_extent"]
+    rot = np.array([0, 1, 0, -1, 0, 0, 0, 0, 1], dtype=np.float64)
+    sc["emitters"] = [dict(width=4, height=3, position=(0.3 * he[0], 1.2 * he[1], 0.0), rotation=rot, velocity=2.0, emit_start=0.0, emit_end=0.03),
+                      dict(width=2, height=2, position=(0.6 * he[0], 1.1 * he[1], 0.1), rotation=rot, velocity=3.0, emit_start=0.004, emit_end=0.02)]
+    gpu, orc = build_pair(gpu_factory, oracle_factory, sc, max_emitted_particles=200, cfl_max_time_step=0.002, target_time=1.0,
+                          surface_tension_method=2, surface_tension=0.5)
+    n0 = gpu.num_fluid
+    for s in range(20):
+        gpu.step(1)
+        orc.step(1)
+        assert gpu.num_fluid == orc.num_fluid, s
+        compare_step(gpu, orc, sc, state_tol=1e-6)
+    assert gpu.num_fluid > n0
+    compare_neighbors(gpu, orc, sc)
+
+
 def test_emitter_capacity_is_respected(gpu_factory, oracle_factory):
     sc = scenes.dam_break_scene(1500, n_boxes=0)
     he = sc["tank_half_extent"]

@@ -1,0 +1,121 @@
+"""Runs the REFERENCE's own optimisation script, unmodified, against this repository's `pysplishsplash` module.
+
+  stage (build container, /root/reference present):
+      python tools/run_reference_script.py stage
+          copies experiments/rigid_body_trajectory_optimization/{python/gradient-based-optimize.py, python/utils.py,
+          scene/diff-bottle-model-collide.json, models/{UnitBox,bottle}.obj, state/bottle_flip/*} into gpurun_in/refscript/
+          - a git-ignored scratch directory that only exists to carry the files to the GPU box (the reference checkout
+          does not exist there); delete it after the run.  Nothing of it is committed.
+  run (GPU box):
+      python tools/run_reference_script.py run [out_dir]
+          1. BASELINE.json configs[2]: gradient-based-optimize.py --taskType bottle-flip on diff-bottle-model-collide.json +
+             state_54 for ONE gradient iteration (--maxIter 0: the script quits after its first optimiser step), with
+             PYTHONPATH = tests/standins (quaternion stand-in) : difffr_b200 (pysplishsplash) : the script's directory;
+          2. the same trajectory driven directly through the C ABI (difffr_b200.cabi) with the scene parsed by the same
+             host loader; loss and gradients are formed the way the script forms them (position_loss / rotation_loss /
+             Simulator_layer_v / Simulator_layer_omega with the gradient manager) and compared with what the script
+             logged.  Both use the same library, so they must agree to the printed digits.
+"""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGE = os.path.join(ROOT, "gpurun_in", "refscript")
+REF = "/root/reference/experiments/rigid_body_trajectory_optimization"
+FILES = ["python/gradient-based-optimize.py", "python/utils.py", "scene/diff-bottle-model-collide.json", "models/UnitBox.obj", "models/bottle.obj",
+         "state/bottle_flip/state_54.bin", "state/bottle_flip/state_54_particle_Fluid.bgeo"]
+
+
+def stage():
+    for f in FILES:
+        dst = os.path.join(STAGE, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, f), dst)
+    print("staged", len(FILES), "files under", STAGE, "(scratch; remove after the GPU run)")
+
+
+def numbers(text):
+    return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", text)]
+
+
+def run(out_dir):
+    os.makedirs(out_dir, exist_ok=True)
+    script = os.path.join(STAGE, "python", "gradient-based-optimize.py")
+    scene = os.path.join(STAGE, "scene", "diff-bottle-model-collide.json")
+    state = os.path.join(STAGE, "state", "bottle_flip", "state_54.bin")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "standins"), os.path.join(ROOT, "difffr_b200"), os.path.dirname(script)])
+    sim_out = os.path.join(out_dir, "script_output")
+    shutil.rmtree(sim_out, ignore_errors=True)
+    cmd = [sys.executable, script, "--scene", scene, "--state", state, "--no-gui", "--no-initial-pause", "--stopAt", "100", "--maxIter", "0",
+           "--taskType", "bottle-flip", "--output-dir", sim_out]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    open(os.path.join(out_dir, "script_stdout.txt"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    log = open(os.path.join(sim_out, "log", "SPH_log.txt")).read()
+    strip = re.compile(r"\x1b\[[0-9;]*m")
+    log = strip.sub("", log)
+    got = {}
+    for key in ("loss_x", "loss_rotation", "loss", "grad_init_v_rb", "grad_init_omega_rb"):
+        m = re.findall(rf"\b{key} = ([^\n]*(?:\n[^\n=]*)?)", log)
+        if m:
+            got[key] = numbers(m[0])[: (1 if key.startswith("loss") else 3)]
+    print("script exit code", r.returncode, "logged:", got)
+
+    # ---- the same iteration through the C ABI ----
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "difffr_b200"))
+    import pysplishsplash as sph
+    from difffr_b200.cabi import Config, Context
+
+    sc = sph._load_scene_full(scene, "")
+    st = sph._read_bgeo(os.path.join(STAGE, "state", "bottle_flip", "state_54_particle_Fluid.bgeo"))
+    cfg = Config.from_buffer_copy(sc["config"])
+    ctx = Context(config=cfg, device=0)
+    ctx.set_fluid(sc["fluid_x"], sc["fluid_v"])
+    for b in sc["bodies"]:
+        ctx.add_body(b["samples"], bool(b["dynamic"]), float(b["density"]), b["translation"], b["rotation"])
+    for i, b in enumerate(sc["bodies"]):
+        if b["dynamic"]:
+            ctx.set_init_v_omega(i, b["init_v"], b["init_omega"])
+    ctx.finalize()
+    ctx.set_gradient_mode(1)
+    ctx.load_fluid_state(st["x"], st["v"], st["kappa"], st["kappa_v"])
+    steps = ctx.run_trajectory(100000)
+    body = 1
+    s = ctx.body_state(body)
+    d = sph._load_scene_summary(scene, "")
+    target_x = np.array(d["bodies"][body]["target_x"]) if "bodies" in d and "target_x" in d["bodies"][body] else None
+    res = {"steps": int(steps), "x": s["x"].tolist(), "q": s["q"].tolist(), "script": got, "script_exit_code": r.returncode}
+    gx_v0, gx_w0 = ctx.manager_grad(body, body, 0), ctx.manager_grad(body, body, 1)
+    gq_v0, gq_w0 = ctx.manager_grad(body, body, 2), ctx.manager_grad(body, body, 3)
+    res["manager_grad_x_to_v0"] = gx_v0.tolist()
+    if target_x is not None:
+        gl = s["x"] - target_x
+        res["loss_x"] = float(0.5 * np.dot(gl, gl))
+        res["grad_init_v_rb"] = (gx_v0.T @ gl).tolist()
+    json.dump(res, open(os.path.join(out_dir, "reference_script_run.json"), "w"), indent=1)
+    print(json.dumps(res)[:1500])
+    ok = True
+    if "loss_x" in got and "loss_x" in res:
+        rel = abs(got["loss_x"][0] - res["loss_x"]) / max(abs(res["loss_x"]), 1e-300)
+        print("loss_x: script", got["loss_x"][0], "C ABI", res["loss_x"], "rel diff", rel)
+        ok &= rel < 1e-9
+    if "grad_init_v_rb" in got and "grad_init_v_rb" in res:
+        a, b_ = np.array(got["grad_init_v_rb"]), np.array(res["grad_init_v_rb"])
+        rel = float(np.max(np.abs(a - b_)) / max(np.max(np.abs(b_)), 1e-300))
+        print("grad_init_v_rb: script", a, "C ABI", b_, "rel diff", rel)
+        ok &= rel < 1e-6  # the log prints ~8 significant digits
+    print("REFERENCE_SCRIPT_OK" if ok and r.returncode == 0 else "REFERENCE_SCRIPT_MISMATCH")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "stage":
+        stage()
+    else:
+        run(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "refscript"))
