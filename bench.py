@@ -260,6 +260,53 @@ def workload_config(n_gpus, mode="slab"):
             "particles_per_gpu": N_PARTICLES, "rollouts": n_gpus, "parallelism": f"independent rollouts x{n_gpus}", "l2": l2}
 
 
+def stone_skipping_iteration(device, torch):
+    """BASELINE.json's third figure on the scene it is defined on: the wall time of ONE gradient iteration of stone
+    skipping (configs[0]; diff-stone-skipping.json as parsed and sampled by the host loader, with the regenerated settled
+    fluid - the inputs of the whole-trajectory parity test, tests/golden/trajectory/).  Timed: dfr_reset + the trajectory
+    to its end (dfr_run_trajectory: ~1,460 CFL-limited steps of 237,699 particles) + the final state and the eight
+    sensitivity blocks.  The authors' log of the same iteration (float32 CPU build, their workstation):
+    497 s (raw_record_and_plot/stone_skipping/2023-05-19-stone-skipping-ours/log/SPH_log.txt:29-44)."""
+    from difffr_b200.cabi import Config, Context
+
+    traj = os.path.join(ROOT, "tests", "golden", "trajectory")
+    f_rec, f_x = os.path.join(traj, "traj_stone_skipping.npz"), os.path.join(traj, "stone_skipping_settled.npz")
+    if not (os.path.exists(f_rec) and os.path.exists(f_x)):
+        return None
+    g = np.load(f_rec)
+    x0 = np.load(f_x)["x"].astype(np.float64)
+    ctx = Context(config=Config.from_buffer_copy(g["config_bytes"].tobytes()), device=device)
+    ctx.set_fluid(x0, np.zeros_like(x0))
+    nb = int(g["n_bodies"])
+    for i in range(nb):
+        ctx.add_body(g[f"body{i}_samples"], bool(g[f"body{i}_dynamic"]), float(g[f"body{i}_density"]), g[f"body{i}_translation"], g[f"body{i}_rotation"])
+    dyn = [i for i in range(nb) if int(g[f"body{i}_dynamic"])]
+    for i in dyn:
+        ctx.set_init_v_omega(i, g[f"body{i}_init_v"], g[f"body{i}_init_omega"])
+    ctx.finalize()
+    ctx.load_fluid_state(x0, np.zeros_like(x0), None, None)
+    ctx.run_trajectory(100000)  # warm-up iteration (graph capture, list capacities)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.reset()
+    done = ctx.run_trajectory(100000)
+    for b in dyn:
+        ctx.body_state(b)
+        for w in range(8):
+            ctx.body_grad(b, w)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    info = ctx.step_info()
+    out = {"seconds": dt, "steps": int(done), "fluid_particles": ctx.num_fluid, "ms_per_step": 1e3 * dt / max(int(done), 1),
+           "mean_pressure_iterations": info.total_pressure_iterations / max(int(done), 1),
+           "authors_log_seconds": 497.0,
+           "what": "BASELINE.json configs[0], stone skipping: dfr_reset + dfr_run_trajectory to the end of the trajectory + final state and "
+                   "sensitivity blocks on diff-stone-skipping.json with the regenerated settled fluid (tests/golden/trajectory/); "
+                   "authors_log_seconds = the same iteration in the reference's own log (float32 CPU build on the authors' workstation)"}
+    ctx.close()
+    return out
+
+
 def pysplishsplash_leg(scene, steps, device):
     """K steps through difffr_b200.pysplishsplash: SimulatorBase.runSimulation() with a per-step Python callback."""
     pkg = os.path.join(ROOT, "difffr_b200")
@@ -630,6 +677,8 @@ def main():
     # read-back per step like the scripts' per-step callback) + the read of the final state and the eight blocks
     gradient_iteration = None
     if world == 1 and not args.no_iteration_leg:
+        gradient_iteration = stone_skipping_iteration(local_rank, torch)
+    if world == 1 and not args.no_iteration_leg and gradient_iteration is None:  # fixtures absent: synthetic stand-in of that size
         n_it, steps_it = 237699, 1450
         sc_it = make_scene(n_it)
         cfg_it = dict(CFG)

@@ -112,17 +112,38 @@ constexpr double kSampleSpacingInRadii = 1.35;
 // (Utilities/PoissonDiskSampling.cpp, random: 159,496 vs 159,284 samples for the same scene on two hosts)
 // and plays the role of RegularTriangleSampling (samplingMode 1): each triangle is covered by a barycentric lattice,
 // then samples closer than 0.85 * spacing to an accepted one are dropped (hash grid, first come first kept).
+// Interior lattice points are displaced inside the triangle's plane by a deterministic pseudo-random offset of up to
+// 0.2 spacings (a hash of the point's running index; corners and edges stay put so that neighbouring triangles still
+// de-duplicate): like the Poisson-disk samples it stands in for, the result has no exact symmetries.  That matters for the
+// penalty contact solver, whose friction Jacobian divides by |x_r - centroid of r's own-body neighbours|
+// (RigidContactSolver.cpp:483-505) - exactly zero for a particle in the middle of a regularly sampled flat face, NaN in
+// the reference's own code as well, and never zero with its random samples.
 inline std::vector<double> sample_mesh(const Mesh &m, double spacing) {
   std::vector<Vec3> cand;
   auto sub = [](const Vec3 &a, const Vec3 &b) { return Vec3{a[0] - b[0], a[1] - b[1], a[2] - b[2]}; };
   auto len = [](const Vec3 &a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+  auto unit01 = [](uint64_t k) {  // splitmix64 -> [0, 1)
+    k += 0x9e3779b97f4a7c15ull;
+    k = (k ^ (k >> 30)) * 0xbf58476d1ce4e5b9ull;
+    k = (k ^ (k >> 27)) * 0x94d049bb133111ebull;
+    k ^= k >> 31;
+    return (double)(k >> 11) * (1.0 / 9007199254740992.0);
+  };
+  uint64_t serial = 0;
   for (const auto &t : m.f) {
     const Vec3 &A = m.v[t[0]], &B = m.v[t[1]], &C = m.v[t[2]];
     const double lmax = std::max(len(sub(B, A)), std::max(len(sub(C, A)), len(sub(C, B))));
     const int n = std::max(1, (int)std::ceil(lmax / spacing));
     for (int i = 0; i <= n; i++)
       for (int j = 0; j <= n - i; j++) {
-        const double u = (double)i / n, w = (double)j / n, s = 1.0 - u - w;
+        double u = (double)i / n, w = (double)j / n;
+        serial++;
+        if (i > 0 && j > 0 && i + j < n) {  // interior point: jitter in barycentric coordinates (stays inside the triangle)
+          const double amp = 0.2 / n;
+          u += amp * (2.0 * unit01(2 * serial) - 1.0);
+          w += amp * (2.0 * unit01(2 * serial + 1) - 1.0);
+        }
+        const double s = 1.0 - u - w;
         cand.push_back({s * A[0] + u * B[0] + w * C[0], s * A[1] + u * B[1] + w * C[1], s * A[2] + u * B[2] + w * C[2]});
       }
   }

@@ -36,6 +36,7 @@ REF = "/root/reference/experiments/rigid_body_trajectory_optimization"
 SCENES = {
     # name: (scene file, settle time [s], max steps of the record)
     "stone_skipping": ("diff-stone-skipping.json", 1.6, 4000),
+    "water_rafting": ("diff-water-rafting-bunny.json", 1.6, 1000),  # BASELINE.json configs[1]; only `dump` is used for it
 }
 GRAD_EVERY = 25
 

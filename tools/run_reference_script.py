@@ -6,6 +6,12 @@
           scene/diff-bottle-model-collide.json, models/{UnitBox,bottle}.obj, state/bottle_flip/*} into gpurun_in/refscript/
           - a git-ignored scratch directory that only exists to carry the files to the GPU box (the reference checkout
           does not exist there); delete it after the run.  Nothing of it is committed.
+  optimise (GPU box):
+      python tools/run_reference_script.py optimise stone|water [out_dir]
+          the README's command for that task (README.md:62-78) with a bounded --maxIter: stone skipping (BASELINE.json
+          configs[0]) for one gradient iteration on the regenerated settled state; water rafting (configs[1]) with Adam,
+          lr 0.1 as in the authors' log (raw_record_and_plot/water_rafting/2023-05-14-dambreak-bunny-ours) for 25 iterations
+          after settling its fluid on the GPU.  Loss per iteration and wall time go to reference_script_<task>.json.
   run (GPU box):
       python tools/run_reference_script.py run [out_dir]
           1. BASELINE.json configs[2]: gradient-based-optimize.py --taskType bottle-flip on diff-bottle-model-collide.json +
@@ -28,8 +34,33 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGE = os.path.join(ROOT, "gpurun_in", "refscript")
 REF = "/root/reference/experiments/rigid_body_trajectory_optimization"
-FILES = ["python/gradient-based-optimize.py", "python/utils.py", "scene/diff-bottle-model-collide.json", "models/UnitBox.obj", "models/bottle.obj",
-         "state/bottle_flip/state_54.bin", "state/bottle_flip/state_54_particle_Fluid.bgeo"]
+FILES = ["python/gradient-based-optimize.py", "python/utils.py", "scene/diff-bottle-model-collide.json", "scene/diff-stone-skipping.json",
+         "scene/diff-water-rafting-bunny.json", "models/UnitBox.obj", "models/bottle.obj", "models/sphere.obj", "models/bunny-fix.obj",
+         "state/bottle_flip/state_54.bin", "state/bottle_flip/state_54_particle_Fluid.bgeo", "state/stone_skipping/state_18.bin",
+         "state/water_rafting/state_130.bin"]
+# the README's commands (README.md:62-78) with a bounded number of optimiser iterations
+TASKS = {
+    "bottle": dict(scene="diff-bottle-model-collide.json", state="bottle_flip/state_54.bin", args=["--taskType", "bottle-flip", "--maxIter", "0"]),
+    "stone": dict(scene="diff-stone-skipping.json", state="stone_skipping/state_18.bin",
+                  args=["--load-fluid-pos", "--taskType", "stone-skipping", "--maxIter", "0"]),
+    "water": dict(scene="diff-water-rafting-bunny.json", state="water_rafting/state_130.bin",
+                  args=["--load-fluid-pos-and-vel", "--taskType", "water-rafting", "--optimizer", "adam", "--lr-v", "0.1", "--lr-omega", "0.1",
+                        "--patience", "10", "--maxIter", "24"]),
+}
+
+
+def write_state_bgeo(task, x):
+    """The particle file the scripts' --state argument implies (state_<n>_particle_Fluid.bgeo beside state_<n>.bin), from
+    regenerated settled positions; velocities and warm-start stiffnesses zero.  Written with this repository's partio
+    Bgeo writer (difffr_b200/host/state_io.hpp)."""
+    sys.path.insert(0, os.path.join(ROOT, "difffr_b200"))
+    import pysplishsplash as sph
+
+    stem = os.path.join(STAGE, "state", TASKS[task]["state"])[: -len(".bin")]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    sph._write_bgeo(stem + "_particle_Fluid.bgeo", x, np.zeros_like(x), np.zeros(n), np.zeros(n))
+    print("wrote", stem + "_particle_Fluid.bgeo", n, "particles")
 
 
 def stage():
@@ -37,6 +68,11 @@ def stage():
         dst = os.path.join(STAGE, f)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         shutil.copyfile(os.path.join(REF, f), dst)
+    # stone skipping: the settled state of the trajectory golden
+    write_state_bgeo("stone", np.load(os.path.join(ROOT, "tests", "golden", "trajectory", "stone_skipping_settled.npz"))["x"])
+    # water rafting: its fluid is settled on the GPU box first (tools/settle_scene.py); the scene as arrays travels with the stage
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_trajectory_golden.py"), "dump", "water_rafting",
+                    os.path.join(ROOT, "gpurun_in", "water_rafting_scene.npz")], check=True)
     print("staged", len(FILES), "files under", STAGE, "(scratch; remove after the GPU run)")
 
 
@@ -44,22 +80,52 @@ def numbers(text):
     return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", text)]
 
 
-def run(out_dir):
+def run_script(task, out_dir):
     os.makedirs(out_dir, exist_ok=True)
+    T = TASKS[task]
     script = os.path.join(STAGE, "python", "gradient-based-optimize.py")
-    scene = os.path.join(STAGE, "scene", "diff-bottle-model-collide.json")
-    state = os.path.join(STAGE, "state", "bottle_flip", "state_54.bin")
+    scene = os.path.join(STAGE, "scene", T["scene"])
+    state = os.path.join(STAGE, "state", T["state"])
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "standins"), os.path.join(ROOT, "difffr_b200"), os.path.dirname(script)])
     sim_out = os.path.join(out_dir, "script_output")
     shutil.rmtree(sim_out, ignore_errors=True)
-    cmd = [sys.executable, script, "--scene", scene, "--state", state, "--no-gui", "--no-initial-pause", "--stopAt", "100", "--maxIter", "0",
-           "--taskType", "bottle-flip", "--output-dir", sim_out]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
-    open(os.path.join(out_dir, "script_stdout.txt"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    cmd = [sys.executable, script, "--scene", scene, "--state", state, "--no-gui", "--no-initial-pause", "--stopAt", "100",
+           "--output-dir", sim_out] + T["args"]
+    import time
+    t0 = time.time()
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
+    wall = time.time() - t0
+    open(os.path.join(out_dir, "script_stdout.txt"), "w").write(" ".join(cmd) + "\n" + r.stdout + "\n---- stderr ----\n" + r.stderr)
     log = open(os.path.join(sim_out, "log", "SPH_log.txt")).read()
-    strip = re.compile(r"\x1b\[[0-9;]*m")
-    log = strip.sub("", log)
+    log = re.compile(r"\x1b\[[0-9;]*m").sub("", log)
+    open(os.path.join(out_dir, "SPH_log.txt"), "w").write(log)
+    return r, log, wall, scene
+
+
+def run_optimisation(task, out_dir):
+    """Several optimiser iterations of the unmodified script: the loss per iteration and the wall time."""
+    if task == "water":  # settle the fluid around the parked bunny first, then hand the script its particle file
+        settled = os.path.join(out_dir, "water_rafting_settled.npz")
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "settle_scene.py"), os.path.join(ROOT, "gpurun_in", "water_rafting_scene.npz"),
+                        settled, "5", "500", "1500"], check=True)
+        write_state_bgeo("water", np.load(settled)["x"])
+    r, log, wall, _ = run_script(task, out_dir)
+    losses = [numbers(m)[0] for m in re.findall(r"\bloss = ([^\n]*)", log)]
+    losses = losses[:: 2] if task != "stone" else losses  # two layers (v, omega) log the same loss once each per iteration
+    steps = [int(numbers(m)[0]) for m in re.findall(r"total timestep of a trajectory = ([^\n]*)", log)]
+    grads = re.findall(r"(grad_[a-z_]+ = \[[^\]]*\])", log)
+    res = {"task": task, "command_args": TASKS[task]["args"], "script_exit_code": r.returncode, "wall_seconds": wall, "iterations": len(losses),
+           "seconds_per_iteration": wall / max(len(losses), 1), "loss_per_iteration": losses, "trajectory_steps": steps[:3],
+           "first_iteration_gradients": grads[:4]}
+    json.dump(res, open(os.path.join(out_dir, f"reference_script_{task}.json"), "w"), indent=1)
+    print(json.dumps(res)[:2500])
+    print("REFERENCE_SCRIPT_OK" if r.returncode == 0 and losses and all(np.isfinite(losses)) else "REFERENCE_SCRIPT_PROBLEM")
+
+
+def run(out_dir):
+    r, log, wall, scene = run_script("bottle", out_dir)
     got = {}
     for key in ("loss_x", "loss_rotation", "loss", "grad_init_v_rb", "grad_init_omega_rb"):
         m = re.findall(rf"\b{key} = ([^\n]*(?:\n[^\n=]*)?)", log)
@@ -75,6 +141,7 @@ def run(out_dir):
 
     sc = sph._load_scene_full(scene, "")
     st = sph._read_bgeo(os.path.join(STAGE, "state", "bottle_flip", "state_54_particle_Fluid.bgeo"))
+    state = os.path.join(STAGE, "state", TASKS["bottle"]["state"])
     cfg = Config.from_buffer_copy(sc["config"])
     ctx = Context(config=cfg, device=0)
     ctx.set_fluid(sc["fluid_x"], sc["fluid_v"])
@@ -117,5 +184,7 @@ def run(out_dir):
 if __name__ == "__main__":
     if sys.argv[1] == "stage":
         stage()
-    else:
+    elif sys.argv[1] == "run":
         run(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "refscript"))
+    else:  # optimise <stone|water> [out_dir]
+        run_optimisation(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "refscript_" + sys.argv[2]))
