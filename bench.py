@@ -540,14 +540,22 @@ def main():
     # ---- end to end through the C ABI with host buffers: one "gradient iteration" ----
     # H2D: the trajectory's initial fluid state (x, v, kappa, kappa_v: 64 B/particle, pinned) + per-step rigid control
     # input; D2H: per-step rigid state and the eight sensitivity blocks (what the optimisation scripts read per step).
-    x_h = torch.from_numpy(np.ascontiguousarray(scene["fluid"])).pin_memory()
+    # A slab-decomposed rank holds (and uploads) its own rows of the scene's arrays: dfr_slab_local_ids /
+    # dfr_load_fluid_state_local.  (Round 1 handed every rank the whole scene and let it pick its rows on the host.)
+    ids = ctx.slab_local_ids() if slab else None
+    x_src = scene["fluid"][ids] if slab else scene["fluid"]
+    n_rows = x_src.shape[0]
+    x_h = torch.from_numpy(np.ascontiguousarray(x_src)).pin_memory()
     v_h = torch.zeros_like(x_h).pin_memory()
-    k_h = torch.zeros(nf, dtype=torch.float64).pin_memory()
-    kv_h = torch.zeros(nf, dtype=torch.float64).pin_memory()
+    k_h = torch.zeros(n_rows, dtype=torch.float64).pin_memory()
+    kv_h = torch.zeros(n_rows, dtype=torch.float64).pin_memory()
     e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
-    ctx.load_fluid_state(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())  # also resets the context
+    if slab:
+        ctx.load_fluid_state_local(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())  # also resets the context
+    else:
+        ctx.load_fluid_state(x_h.numpy(), v_h.numpy(), k_h.numpy(), kv_h.numpy())
     t_load = time.perf_counter() - t0
     d2h = 0
     for k in range(e2e_steps):
@@ -562,7 +570,7 @@ def main():
                 ctx.body_grad(b, w)
     barrier()
     e2e_wall = time.perf_counter() - t0
-    h2d_per_step = (64 * nf) / e2e_steps + 48 * len(dyn)
+    h2d_per_step = (64 * n_rows) / e2e_steps + 48 * len(dyn)  # per rank
     d2h_per_step = len(dyn) * (13 + 4 * 9 + 2 * 12 + 2 * 9) * 8 + 8 * 40
     e2e_psteps = nf * e2e_steps
     slab_info = ctx.slab_info() if slab else None
@@ -726,8 +734,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_psteps_all / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms / e2e_steps, "load_state_ms_rank0": 1e3 * t_load,
-                "what": "dfr_load_fluid_state from pinned host arrays + per step: dfr_set_init_v_omega, dfr_step(1), "
-                        "dfr_get_body_state + 8x dfr_get_body_grad per dynamic body"},
+                "what": "dfr_load_fluid_state (slab: dfr_load_fluid_state_local, each rank its own rows) from pinned host arrays + per step: "
+                        "dfr_set_init_v_omega, dfr_step(1), dfr_get_body_state + 8x dfr_get_body_grad per dynamic body; byte counts per rank"},
         "gpu_launches": int(launches_all),
         "slab": ({"owned_rank0": slab_info["owned"], "ghosts_rank0": slab_info["ghosts"], "ghost_transport": slab_info["transport"],
                   "nvlink_bytes_per_step_rank0": slab_info["exchanged_bytes"] / max(e2e_steps, 1)} if slab else None),

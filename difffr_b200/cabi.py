@@ -95,7 +95,7 @@ SYMBOLS = [
     "get_step_info", "get_body_state", "set_body_velocity", "get_body_properties",
     "get_body_grad", "get_manager_grad", "download_fluid", "download_body", "num_fluid", "num_fluid_initial",
     "num_body_particles", "num_bodies", "get_neighbors", "add_emitter", "get_device_time_ms",
-    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_plan", "slab_unique_id", "slab_configure", "slab_info",
+    "set_profiling", "get_kernel_profile", "reset_gradient", "set_gradient_mode", "slab_plan", "slab_unique_id", "slab_configure", "slab_info", "slab_local_ids", "load_fluid_state_local",
 ]
 
 GRAD_NAMES = [
@@ -230,6 +230,8 @@ class Context:
             proto("slab_unique_id", C.c_int, C.c_char_p)
             proto("slab_configure", C.c_int, vp, C.c_int, C.c_int, C.c_char_p)
             proto("slab_info", C.c_int, vp, C.POINTER(i64))
+            proto("slab_local_ids", i64, vp, ip, i64)
+            proto("load_fluid_state_local", C.c_int, vp, i64, dp, dp, dp, dp)
         proto("reset_gradient", C.c_int, vp)
         proto("set_gradient_mode", C.c_int, vp, C.c_int)
         if hasattr(L, p + "set_profiling"):  # the CPU oracle has no kernels to profile
@@ -301,6 +303,21 @@ class Context:
 
     def finalize(self):
         self._check(self._fn("finalize")(self._ctx))
+
+    def slab_local_ids(self):
+        """Particle ids (rows of the scene's arrays) this context held at t = 0: the rows load_fluid_state_local takes."""
+        n = int(self._fn("slab_local_ids")(self._ctx, None, 0))
+        ids = np.zeros(n, dtype=np.int32)
+        self._fn("slab_local_ids")(self._ctx, ids.ctypes.data_as(C.POINTER(C.c_int32)), n)
+        return ids
+
+    def load_fluid_state_local(self, x=None, v=None, kappa=None, kappa_v=None):
+        x, v, k, kv = _f64(x), _f64(v), _f64(kappa), _f64(kappa_v)
+        n = int(self._fn("slab_local_ids")(self._ctx, None, 0))
+        for name, a, width in (("x", x, 3), ("v", v, 3), ("kappa", k, 1), ("kappa_v", kv, 1)):
+            if a is not None and a.size != width * n:
+                raise ValueError(f"load_fluid_state_local: {name} holds {a.size} values, this context's {n} rows need {width * n}")
+        self._check(self._fn("load_fluid_state_local")(self._ctx, n, _dptr(x), _dptr(v), _dptr(k), _dptr(kv)))
 
     def load_fluid_state(self, x=None, v=None, kappa=None, kappa_v=None):
         x, v, k, kv = _f64(x), _f64(v), _f64(kappa), _f64(kappa_v)

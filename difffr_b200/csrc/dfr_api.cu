@@ -2013,11 +2013,28 @@ int dfr_finalize(dfr_context *c) {
   return DFR_OK;
 }
 
+int64_t dfr_slab_local_ids(dfr_context *c, int32_t *ids_out, int64_t capacity) {
+  if (!c || !c->finalized) return 0;
+  const int64_t n = c->nf_loc0;
+  if (ids_out)
+    for (int64_t k = 0; k < n && k < capacity; k++) ids_out[k] = c->slab.on ? c->h_ids0[k] : (int32_t)k;
+  return n;
+}
+
+static int load_fluid_state_impl(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v, bool local_rows);
+int dfr_load_fluid_state_local(dfr_context *c, int64_t n, const double *x, const double *v, const double *kappa, const double *kappa_v) {
+  if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
+  if (n != c->nf_loc0) return fail(c, DFR_ERR_INVALID, "dfr_load_fluid_state_local: n differs from the rows this context holds (dfr_slab_local_ids)");
+  return load_fluid_state_impl(c, x, v, kappa, kappa_v, true);
+}
 int dfr_load_fluid_state(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v) {
+  return load_fluid_state_impl(c, x, v, kappa, kappa_v, false);
+}
+static int load_fluid_state_impl(dfr_context *c, const double *x, const double *v, const double *kappa, const double *kappa_v, bool local_rows) {
   if (!c || !c->finalized) return fail(c, DFR_ERR_STATE, "not finalized");
   cudaSetDevice(c->device);
   const int64_t n = c->nf_loc0;  // arrays are indexed by particle id; a slab keeps the ids it owned at t = 0
-  if (!c->slab.on) {
+  if (!c->slab.on || local_rows) {
     // straight from the caller's (ideally pinned) arrays: H2D into scratch, repack on the device
     double *stage = (double *)c->acc.p;  // n double4 of scratch >= 3 n doubles; reset clears it afterwards
     if (x && n) {

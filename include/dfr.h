@@ -150,6 +150,14 @@ int dfr_finalize(dfr_context *ctx);
 int dfr_load_fluid_state(dfr_context *ctx, const double *x, const double *v,
                          const double *kappa, const double *kappa_v);
 
+/* The same for the rows THIS context holds (slab-decomposed contexts; on a single context identical to
+ * dfr_load_fluid_state): dfr_slab_local_ids gives the particle ids (rows of the scene's arrays) the context held at t = 0,
+ * n of them (returned; ids_out may be NULL to ask for n only), and dfr_load_fluid_state_local takes arrays of exactly those
+ * rows in that order - a rank of a distributed job uploads its share instead of gathering from whole-scene arrays. */
+int64_t dfr_slab_local_ids(dfr_context *ctx, int32_t *ids_out, int64_t capacity);
+int dfr_load_fluid_state_local(dfr_context *ctx, int64_t n, const double *x, const double *v, const double *kappa,
+                               const double *kappa_v);
+
 /* SimulatorBase::reset (SimulatorBase.cpp:887-934). */
 int dfr_reset(dfr_context *ctx);
 

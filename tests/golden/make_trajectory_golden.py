@@ -14,6 +14,7 @@ the column has collapsed to its rest height, and the positions are kept as float
   python tests/golden/make_trajectory_golden.py record stone_skipping     -> tests/golden/trajectory/traj_stone_skipping.npz
   python tests/golden/make_trajectory_golden.py record stone_skipping orc -> /tmp/traj_stone_skipping_orc.npz (the oracle
       port on the same inputs: how far two FP-different CPU implementations drift over the trajectory)
+  python tests/golden/make_trajectory_golden.py drift stone_skipping      -> tests/golden/trajectory/stone_skipping_cpu_drift.npz
 
 The record holds the complete inputs except the fluid positions (the settled file), per step the rigid state, time step
 and iteration counts, and every GRAD_EVERY steps plus at the end of the trajectory the 16 Jacobian / sensitivity blocks.
@@ -148,6 +149,35 @@ def record(name, lib_kind="ref"):
     print("wrote", path, os.path.getsize(path), "bytes,", len(states), "steps")
 
 
+def drift(name):
+    """tests/golden/trajectory/<name>_cpu_drift.npz: the oracle port's record against the reference's, step by step."""
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    r, o = np.load(os.path.join(HERE, f"traj_{name}.npz")), np.load(f"/tmp/traj_{name}_orc.npz")
+    n = min(len(r["body_state"]), len(o["body_state"]))
+    sl4 = (slice(0, 3), slice(3, 7), slice(7, 10), slice(10, 13))
+    err = np.array([[rel(o["body_state"][s][sl], r["body_state"][s][sl]) for sl in sl4] for s in range(n)])
+    dh = np.abs(o["step_h"][:n] - r["step_h"][:n]) / r["step_h"][:n]
+    tgt = np.array([1.7, 1.6, 0.0])
+
+    def lg(st, g):
+        gx = st[:3] - tgt
+        return np.concatenate([g[0, :9].reshape(3, 3).T @ gx, g[1, :9].reshape(3, 3).T @ gx])
+
+    eo, er, go, gr = o["body_state"][-1], r["body_state"][-1], o["body_grads"][-1], r["body_grads"][-1]
+    os_, rs_ = [int(v) for v in o["grad_steps"]], [int(v) for v in r["grad_steps"]]
+    gs = [s for s in rs_ if s <= n and s in os_]
+    gerr = [[rel(o["body_grads"][os_.index(s)][w], r["body_grads"][rs_.index(s)][w]) for w in range(16)] for s in gs]
+    np.savez_compressed(os.path.join(HERE, f"{name}_cpu_drift.npz"), steps_oracle=len(o["body_state"]), steps_reference=len(r["body_state"]),
+                        state_err=err, h_err=dh, grad_steps=np.array(gs), grad_err=np.array(gerr),
+                        end_state_err=np.array([rel(eo[sl], er[sl]) for sl in sl4]), end_loss_gradient_err=rel(lg(eo, go), lg(er, gr)),
+                        end_loss_gradient_oracle=lg(eo, go), end_loss_gradient_reference=lg(er, gr),
+                        end_sensitivity_err=np.array([rel(go[w], gr[w]) for w in range(16)]),
+                        note="the CPU oracle port against the reference's own code on the same trajectory: how far two FP64 "
+                             "implementations of the same algorithm drift apart")
+
+
 def dump(name, path):
     """The scene as arrays (what tools/settle_scene.py needs on the GPU box, where /root/reference does not exist)."""
     sc, cfg = load(name)
@@ -165,6 +195,8 @@ if __name__ == "__main__":
     cmd, name = sys.argv[1], sys.argv[2]
     if cmd == "dump":
         dump(name, sys.argv[3])
+    elif cmd == "drift":
+        drift(name)
     elif cmd == "settle":
         settle(name)
     else:

@@ -60,7 +60,11 @@ def main():
             st_v = rng.normal(scale=0.1, size=sc["fluid"].shape)
             st_k = -1e-6 * rng.random(n)
             st_kv = -1e-3 * rng.random(n)
-            slab.load_fluid_state(st_x, st_v, st_k, st_kv)
+            if steps % 2 == 0:
+                slab.load_fluid_state(st_x, st_v, st_k, st_kv)
+            else:  # the per-rank form: only the rows this slab held at t = 0, in the order dfr_slab_local_ids gives
+                ids = slab.slab_local_ids()
+                slab.load_fluid_state_local(st_x[ids], st_v[ids], st_k[ids], st_kv[ids])
             if single:
                 single.load_fluid_state(st_x, st_v, st_k, st_kv)
         slab.step(1)

@@ -24,7 +24,8 @@ def test_two_slabs_equal_one_domain(manager, transport):
     if _gpus() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29517 + manager + (4 if transport == "nccl" else 0)), os.path.join(ROOT, "tests", "slab_check.py"), "30000", "6",
+           "--master-port", str(29517 + manager + (4 if transport == "nccl" else 0)), os.path.join(ROOT, "tests", "slab_check.py"), "30000",
+           str(6 + manager),  # an odd step count makes slab_check load a state through the per-rank form
            str(manager)]
     env = dict(os.environ)
     if transport == "nccl":
