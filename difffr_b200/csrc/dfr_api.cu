@@ -2137,27 +2137,30 @@ int relax_list_capacity(dfr_context *c) {
   CU(cudaStreamSynchronize(c->stream));
   const size_t nwarp = ((size_t)c->nf_cap + 31) / 32;
   if (f) {
-    const int want = ((int)(2 * c->hSt->list_used_f) + 8 + 3) & ~3;
+    const int want = ((int)(2 * c->hSt->list_used_f + c->hSt->list_used_f / 2) + 8 + 3) & ~3;  // 2.5x: room to creep up
     if (want > 4096) return DFR_OK;  // stay on the watched stream path
     c->idx_f.free();
     CU(c->idx_f.alloc(nwarp * 32 * (size_t)want));
     c->cap_f = want;
   }
   if (b) {
-    const int want = ((int)(2 * c->hSt->list_used_b) + 8 + 3) & ~3;
+    const int want = ((int)(2 * c->hSt->list_used_b + c->hSt->list_used_b / 2) + 8 + 3) & ~3;
     if (want > 4096) return DFR_OK;
     c->idx_b.free();
     CU(c->idx_b.alloc(nwarp * 32 * (size_t)want));
     c->cap_b = want;
   }
   if (d) {
-    const unsigned long long want = 2ull * c->hSt->list_used_d + 1024;
+    const unsigned long long want = 3ull * c->hSt->list_used_d + 1024;
     if (want > (1ull << 31)) return DFR_OK;
     c->idx_d.free();
     CU(c->idx_d.alloc((size_t)want));
     c->cap_d = (unsigned int)want;
   }
   drop_step_graphs(c);  // the list pointers and capacities are recorded in the graphs
+  if (getenv_int("DFR_DEBUG"))
+    std::fprintf(stderr, "[dfr] step %d: list capacities -> f %d b %d d %u (longest rows f %u b %u, d entries %u)\n", c->hSt->step_count, c->cap_f,
+                 c->cap_b, c->cap_d, c->hSt->list_used_f, c->hSt->list_used_b, c->hSt->list_used_d);
   return DFR_OK;
 }
 int enqueue_steps(dfr_context *c, int n_steps, int gated, StepBatch &B) {
@@ -2179,6 +2182,7 @@ int enqueue_steps(dfr_context *c, int n_steps, int gated, StepBatch &B) {
     const int g = (gated && s > 0) ? 1 : 0;
     dfr_context::StepGraph &sg = c->step_graph[g][c->cur];
     if (!sg.exec) {
+      if (getenv_int("DFR_DEBUG")) std::fprintf(stderr, "[dfr] step %d: recording step graph (gated %d, parity %d)\n", c->hSt->step_count, g, c->cur);
       int rc = capture_step_graph(c, g);
       if (rc) {  // keep working without graphs (the error text stays in last_error until the next failure)
         c->graph_broken = 1;

@@ -40,6 +40,10 @@ SCENES = {
     # configs[1]: the bunny floats from the first step (no ramp, per-body chain rule, no manager); lattice start - the
     # settled state_130 the scripts load is not in the reference repository
     "paper_water_rafting": ("diff-water-rafting-bunny.json", None, 5, {"paper": {}}, 2),
+    # configs[3]: the high-diving scene (118,389 fluid particles, the duck + four static meshes with 296 k samples, the box
+    # emitter firing in the first step, Akinci-2013 surface tension on).  The body samples are rounded to float32 before
+    # BOTH sides use them, which halves the fixture (3.4 MB of the file are those samples).
+    "paper_high_diving": ("diff-high-diving-duck.json", None, 6, {"paper": {}}, 6),
     # (five steps of state, two of sensitivities: the bunny starts inside a perfect lattice whose particles all have
     # rho* = 1 up to rounding, i.e. they sit ON the rho* > 1 gate of the Jacobians (TimeStepDiffDFSPH.cpp:1539).  Which side
     # a particle falls on is rounding noise, so from the third step on the net Jacobians of any two FP-different runs (the
@@ -61,6 +65,9 @@ def run_segment(name, seg):
 
     sph = import_sph()
     sc = sph._load_scene_full(SCENE, "")
+    if name == "paper_high_diving":
+        for bd in sc["bodies"]:
+            bd["samples"] = bd["samples"].astype(np.float32).astype(np.float64)
     st = sph._read_bgeo(os.path.join(REF, "state", state_file)) if state_file else None
     cfg = Config.from_buffer_copy(sc["config"])
     for k, v in SEGMENTS[seg].items():
@@ -71,6 +78,8 @@ def run_segment(name, seg):
     ctx.set_fluid(sc["fluid_x"], sc["fluid_v"])
     for b in sc["bodies"]:
         ctx.add_body(b["samples"], bool(b["dynamic"]), float(b["density"]), b["translation"], b["rotation"])
+    for e in sc["emitters"]:
+        ctx.add_emitter(**e)
     for i, b in enumerate(sc["bodies"]):
         if b["dynamic"]:
             ctx.set_init_v_omega(i, b["init_v"], b["init_omega"])
@@ -85,8 +94,14 @@ def run_segment(name, seg):
                     "n_bodies": len(sc["bodies"]), "steps": STEPS, "grad_steps": GRAD_STEPS, "fluid_step": min(FLUID_STEP, STEPS), "fluid_stride": FLUID_STRIDE, "segments": np.array(list(SEGMENTS.keys()))})
         if st is not None:
             out.update({"state_x": st["x"], "state_v": st["v"], "state_kappa": st["kappa"], "state_kappa_v": st["kappa_v"]})
+        out["n_emitters"] = len(sc["emitters"])
+        for k, e in enumerate(sc["emitters"]):
+            out[f"emitter{k}_wh"] = np.array([e["width"], e["height"]])
+            out[f"emitter{k}_position"] = np.asarray(e["position"], dtype=np.float64)
+            out[f"emitter{k}_rotation"] = np.asarray(e["rotation"], dtype=np.float64)
+            out[f"emitter{k}_vse"] = np.array([e["velocity"], e["emit_start"], e["emit_end"]], dtype=np.float64)
         for i, b in enumerate(sc["bodies"]):
-            out[f"body{i}_samples"] = b["samples"]
+            out[f"body{i}_samples"] = b["samples"].astype(np.float32) if name == "paper_high_diving" else b["samples"]
             out[f"body{i}_dynamic"] = int(b["dynamic"])
             out[f"body{i}_density"] = float(b["density"])
             out[f"body{i}_translation"] = b["translation"]
@@ -101,7 +116,7 @@ def run_segment(name, seg):
     P = seg + "_"
     out[P + "cfg_keys"] = np.array(list(SEGMENTS[seg].keys()))
     out[P + "cfg_vals"] = np.array([float(v) for v in SEGMENTS[seg].values()])
-    rec = {k: [] for k in ("time", "h", "iters", "iters_v", "finished")}
+    rec = {k: [] for k in ("time", "h", "iters", "iters_v", "finished", "num_fluid")}
     states, fts, grads, mgrs = [], [], [], []
     for s in range(STEPS):
         ctx.step(1)
@@ -111,6 +126,7 @@ def run_segment(name, seg):
         rec["iters"].append(info.iterations)
         rec["iters_v"].append(info.iterations_v)
         rec["finished"].append(info.trajectory_finished)
+        rec["num_fluid"].append(info.num_fluid_particles)
         bs = ctx.body_state(b)
         states.append(np.concatenate([bs["x"], bs["q"], bs["v"], bs["omega"]]))
         pr = ctx.body_properties(b)

@@ -121,6 +121,10 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
             ctx.add_body(g[f"body{b}_samples"], bool(g[f"body{b}_dynamic"]), float(g[f"body{b}_density"]), g[f"body{b}_translation"],
                          g[f"body{b}_rotation"])
         dyn = [b for b in range(nb) if int(g[f"body{b}_dynamic"])]
+        for k in range(int(g["n_emitters"]) if "n_emitters" in g.files else 0):
+            wh, vse = g[f"emitter{k}_wh"], g[f"emitter{k}_vse"]
+            ctx.add_emitter(width=int(wh[0]), height=int(wh[1]), position=g[f"emitter{k}_position"], rotation=g[f"emitter{k}_rotation"],
+                            velocity=float(vse[0]), emit_start=float(vse[1]), emit_end=float(vse[2]))
         for b in dyn:
             ctx.set_init_v_omega(b, g[f"body{b}_init_v"], g[f"body{b}_init_omega"])
         ctx.finalize()
@@ -140,6 +144,8 @@ def replay_paper_and_compare(factory, name, state_tol, grad_tol):
             assert abs(info.time - g[P + "step_time"][s]) <= 1e-12 * max(abs(g[P + "step_time"][s]), 1e-30)
             assert abs(info.time_step_size - g[P + "step_h"][s]) <= 1e-10 * g[P + "step_h"][s], (seg, s)
             assert info.trajectory_finished == int(g[P + "step_finished"][s])
+            if P + "step_num_fluid" in g.files:  # emitter scenes: emitted particles
+                assert info.num_fluid_particles == int(g[P + "step_num_fluid"][s]), (seg, s, info.num_fluid_particles)
             st = ctx.body_state(b)
             got = np.concatenate([st["x"], st["q"], st["v"], st["omega"]])
             ref = g[P + "body_state"][s]
