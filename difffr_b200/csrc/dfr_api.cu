@@ -175,8 +175,16 @@ struct dfr_context {
     void *ipc_opened[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> flags;    // [0] raised by the low neighbour, [1] by the high one
     DevBuf<char> ipc_stage;
-    unsigned long long pass = 0;
-    int lo_nb_own_end = 0;               // where my low boundary layer starts in the low neighbour's arrays
+    DevBuf<unsigned long long> seq;      // [0] ghost-update passes signalled, [1] mailbox all-reduces done: on the device, never reset
+    // small all-reduces over peer memory (dfr_slab.cuh: SlabMail): every rank maps every rank's mailbox
+    DevBuf<double> mbox;
+    DevBuf<unsigned long long> mflag;
+    SlabMail mail;
+    bool mail_ok = false;
+    std::vector<void *> ipc_more;
+    long long sync_rows = 0;             // rows one ghost update moves (both directions), from the last exchange
+    int64_t cap_syncs_static = 0, cap_syncs_div = 0, cap_syncs_prs = 0;  // ghost updates per replayed step / iteration
+    int64_t *cap_sync_counter = nullptr;
   } slab;
 
   // SM-local scheduling of the gather kernels (dfr_kernels.cuh: VSched)
@@ -564,7 +572,8 @@ void drop_step_graphs(dfr_context *c) {
     }
 }
 bool graph_stepping_possible(const dfr_context *c) {
-  return !c->graph_broken && !c->slab.on && !c->profiling && getenv_int("DFR_NO_GRAPH") == 0 && getenv_int("DFR_NO_FUSION") != 3;
+  if (c->slab.on && !(c->slab.p2p && c->slab.mail_ok)) return false;  // NCCL transport: collective calls inside the solves
+  return !c->graph_broken && !c->profiling && getenv_int("DFR_NO_GRAPH") == 0 && getenv_int("DFR_NO_FUSION") != 3;
 }
 // Records the step that starts with buffer parity c->cur; `gated` = the step is skipped once the trajectory has finished.
 // Host-side buffer indices are restored afterwards (recording executes nothing).
@@ -572,8 +581,13 @@ int capture_step_graph(dfr_context *c, int gated) {
   dfr_context::StepGraph &sg = c->step_graph[gated][c->cur];
   for (auto &cs : c->cap_stream)
     if (!cs) CUG(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-  const int cur0 = c->cur, vcur0 = c->vcur, parity0 = c->sched_parity;
+  const int cur0 = c->cur, vcur0 = c->vcur, parity0 = c->sched_parity, nf0 = c->launch_nf;
   sg = dfr_context::StepGraph();
+  if (c->slab.on) {  // the number of local particles changes with every exchange: grids for the capacity, kernels test the range
+    c->launch_nf = (int)c->nf_cap;
+    c->slab.cap_syncs_static = c->slab.cap_syncs_div = c->slab.cap_syncs_prs = 0;
+    c->slab.cap_sync_counter = &c->slab.cap_syncs_static;
+  }
   c->capturing = true;
   c->cap_target = &sg;
   c->cap_counter = &sg.n_static;
@@ -604,6 +618,7 @@ int capture_step_graph(dfr_context *c, int gated) {
   c->cur = cur0;
   c->vcur = vcur0;
   c->sched_parity = parity0;
+  c->launch_nf = nf0;
   if (!rc && e != cudaSuccess) rc = fail(c, DFR_ERR_CUDA, std::string("step graph: cudaStreamEndCapture: ") + cudaGetErrorString(e));
   if (rc) {
     if (g) cudaGraphDestroy(g);
@@ -682,16 +697,12 @@ GhostOut ghost_out(dfr_context *c, int which) {
   std::memset(&g, 0, sizeof(g));
   auto &S = c->slab;
   if (!S.on || !S.p2p) return g;
-  if (S.G.has_lo) {
-    g.lo = S.peer_lo[which] + S.lo_nb_own_end;  // the low neighbour's ghost_hi range starts at its own_end
-    g.lo_begin = S.h_ranges[0];
-    g.lo_end = S.h_ranges[2];
-  }
-  if (S.G.has_hi) {
-    g.hi = S.peer_hi[which];  // the high neighbour's ghost_lo range starts at 0
-    g.hi_begin = S.h_ranges[3];
-    g.hi_end = S.h_ranges[1];
-  }
+  // row ranges and the low neighbour's own_end are read on the device (StepState::slab_ranges; S.counts[3] holds what
+  // the low neighbour sent with the layer counts of the last exchange)
+  if (S.G.has_lo) g.lo = S.peer_lo[which];
+  if (S.G.has_hi) g.hi = S.peer_hi[which];
+  g.ranges = c->dSt.p->slab_ranges;
+  g.lo_nb_own_end = S.counts.p + 3;
   return g;
 }
 
@@ -699,13 +710,13 @@ GhostOut ghost_out(dfr_context *c, int which) {
 int slab_sync(dfr_context *c, void *buf, size_t esz) {
   auto &S = c->slab;
   if (S.p2p) {  // the rows were written by the producing kernel; tell the neighbours and wait for theirs
-    S.pass++;
     LAUNCH(c, k_slab_signal_wait, 1, 32, S.G.has_lo ? S.peer_lo_flags + 1 : (unsigned long long *)nullptr,
-           S.G.has_hi ? S.peer_hi_flags + 0 : (unsigned long long *)nullptr, (volatile unsigned long long *)S.flags.p, S.pass,
+           S.G.has_hi ? S.peer_hi_flags + 0 : (unsigned long long *)nullptr, (volatile unsigned long long *)S.flags.p, S.seq.p + 0,
            5000000000ull, &c->dSt.p->error_flags);
-    const long long rows = (S.G.has_lo ? (S.h_ranges[2] - S.h_ranges[0]) + S.h_ranges[0] : 0) +
-                           (S.G.has_hi ? (S.h_ranges[1] - S.h_ranges[3]) + (S.h_ranges[4] - S.h_ranges[1]) : 0);
-    S.exchanged_bytes += rows * (long long)esz;
+    if (c->capturing)
+      (*S.cap_sync_counter)++;  // replayed steps: traffic is accounted from these counts after the step (account_graph_launches)
+    else
+      S.exchanged_bytes += S.sync_rows * (long long)esz;
     return DFR_OK;
   }
   NcclApi *N = nccl_api(nullptr);
@@ -790,13 +801,69 @@ int slab_p2p_setup(dfr_context *c) {
         (side == 0 ? S.peer_lo_flags : S.peer_hi_flags) = (unsigned long long *)ptr;
     }
   }
+  // ---- the mailboxes of ALL ranks: residual sums, the CFL maximum and the per-body rows are all-reduced by one small
+  // kernel over peer memory (dfr_slab.cuh: mailbox_allreduce) instead of a collective launch ----
+  CU(S.seq.alloc(2));
+  const int mcap = std::max<int>(8, (int)std::max<size_t>(c->bodies.size(), 1) * ACC_N);
+  CU(S.mbox.alloc((size_t)2 * S.n * mcap));
+  CU(S.mflag.alloc((size_t)S.n));
+  int mail = (ok && S.n <= DFR_MAX_SLABS) ? 1 : 0;
+  {
+    const size_t hsz = sizeof(cudaIpcMemHandle_t), per = 2 * hsz;
+    std::vector<cudaIpcMemHandle_t> mh(2 * (size_t)(S.n + 1));
+    std::memset(mh.data(), 0, mh.size() * hsz);
+    if (mail && (cudaIpcGetMemHandle(&mh[0], S.mbox.p) != cudaSuccess || cudaIpcGetMemHandle(&mh[1], S.mflag.p) != cudaSuccess)) {
+      cudaGetLastError();
+      mail = 0;
+    }
+    DevBuf<char> mstage;
+    CU(mstage.alloc(per * (size_t)(S.n + 1)));
+    CU(cudaMemcpyAsync(mstage.p, mh.data(), per, cudaMemcpyHostToDevice, c->stream));
+    NC(N->GroupStart());
+    for (int p = 0; p < S.n; p++) {
+      if (p == S.rank) continue;
+      NC(N->Send(mstage.p, per, ncclChar, p, S.comm, c->stream));
+      NC(N->Recv(mstage.p + per * (size_t)(1 + p), per, ncclChar, p, S.comm, c->stream));
+    }
+    NC(N->GroupEnd());
+    CU(cudaMemcpyAsync(mh.data(), mstage.p, per * (size_t)(S.n + 1), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    mstage.free();
+    std::memset(&S.mail, 0, sizeof(S.mail));
+    S.mail.n = S.n;
+    S.mail.rank = S.rank;
+    S.mail.cap = mcap;
+    S.mail.seq = S.seq.p + 1;
+    for (int p = 0; p < S.n && mail; p++) {
+      if (p == S.rank) {
+        S.mail.box[p] = S.mbox.p;
+        S.mail.flag[p] = S.mflag.p;
+        continue;
+      }
+      void *pb = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pb, mh[2 * (size_t)(1 + p)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, mh[2 * (size_t)(1 + p) + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mail = 0;
+        if (pb) S.ipc_more.push_back(pb);
+        break;
+      }
+      S.ipc_more.push_back(pb);
+      S.ipc_more.push_back(pf);
+      S.mail.box[p] = (double *)pb;
+      S.mail.flag[p] = (unsigned long long *)pf;
+    }
+  }
+  if (getenv_int("DFR_SLAB_NO_MAILBOX")) mail = 0;  // A/B: keep the NCCL all-reduces
   // everybody or nobody
   int *flag = (int *)(S.ipc_stage.p + 3 * hb);
-  CU(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  NC(N->AllReduce(flag, flag, 1, ncclInt, ncclMin, S.comm, c->stream));
-  CU(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int both[2] = {ok, mail};
+  CU(cudaMemcpyAsync(flag, both, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NC(N->AllReduce(flag, flag, 2, ncclInt, ncclMin, S.comm, c->stream));
+  CU(cudaMemcpyAsync(both, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  S.p2p = ok != 0;
+  S.p2p = both[0] != 0;
+  S.mail_ok = S.p2p && both[1] != 0;
   return DFR_OK;
 }
 
@@ -897,7 +964,8 @@ int slab_exchange_and_sort(dfr_context *c) {
                   ghost_hi, S.G.has_lo ? S.h_counts[2] : 0, S.G.has_hi ? S.h_counts[4] : 0);
     return fail(c, DFR_ERR_STATE, buf);
   }
-  S.lo_nb_own_end = S.G.has_lo ? S.h_counts[3] : 0;
+  S.sync_rows = (S.G.has_lo ? (S.h_ranges[2] - S.h_ranges[0]) + S.h_ranges[0] : 0) +
+                (S.G.has_hi ? (S.h_ranges[1] - S.h_ranges[3]) + (S.h_ranges[4] - S.h_ranges[1]) : 0);
   return DFR_OK;
 }
 
@@ -985,8 +1053,11 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
     if (!rc) rc = cap_begin_conditional(c, cudaGraphCondTypeWhile, cond);
     if (rc) return rc;
     c->cap_counter = PRESSURE ? &c->cap_target->n_prs_body : &c->cap_target->n_div_body;
+    int64_t *outer_syncs = c->slab.cap_sync_counter;
+    c->slab.cap_sync_counter = PRESSURE ? &c->slab.cap_syncs_prs : &c->slab.cap_syncs_div;
     launch_boundary_side<PRESSURE>(c, true, 1);
     PLAUNCH(c, (k_push<PRESSURE, true>), g, PUSH_ARGS);
+    SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));
     const bool fuse_np = !PRESSURE && fuse_nonpressure;
     if (fuse_np) {
       RhoExtra X = X0;
@@ -999,9 +1070,15 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
       PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS_X(c->pos[a].p, Xp));
     } else
       PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
-    LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
-           cond, fuse_np ? 1 : 0);
+    if (c->slab.on) {  // the stopping rule needs the residual of all slabs: summed over peer memory by the deciding kernel
+      LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
+             0ull, 0);
+      LAUNCH(c, k_slab_residual_decide<PRESSURE>, 1, 64, c->P, c->dSt.p, c->slab.mail, cond, fuse_np ? 1 : 0);
+    } else
+      LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
+             cond, fuse_np ? 1 : 0);
     c->cap_counter = outer_counter;
+    c->slab.cap_sync_counter = outer_syncs;
     // the two gated k_rho launches count as one executed kernel per iteration
     if (fuse_np) c->cap_target->n_div_body -= 1;
     rc = cap_end_conditional(c);
@@ -1034,7 +1111,9 @@ int launch_solver(dfr_context *c, bool fuse_density = false, bool fuse_normals =
         PLAUNCH(c, (k_rho<PRESSURE, RHO_ITER>), g, RHO_ARGS);
       LAUNCH(c, k_residual_finish<PRESSURE>, RES_BLOCKS, RES_THREADS, c->P, c->dSt.p, c->partials.p, c->partials.p + c->partials.n - RES_BLOCKS,
              0ull, 0);
-      if (c->slab.on) {  // the residual of the iteration is the sum over all slabs
+      if (c->slab.on && c->slab.mail_ok) {  // the residual of the iteration is the sum over all slabs: one kernel over peer memory
+        LAUNCH(c, k_slab_residual_decide<PRESSURE>, 1, 64, c->P, c->dSt.p, c->slab.mail, 0ull, 0);
+      } else if (c->slab.on) {
         int rc = slab_allreduce(c, &c->dSt.p->res_sum, 1, ncclDouble, ncclSum);
         if (rc) return rc;
         LAUNCH(c, k_solver_decide<PRESSURE>, 1, 32, c->P, c->dSt.p);
@@ -1211,8 +1290,14 @@ int launch_step(dfr_context *c) {
     rc = contact_sort_tick(c);
     if (rc) return rc;
   }
-  LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, (c->capturing && fuse_nonpressure_enabled(c)) ? 1 : 0);
-  rc = build_neighbors(c);
+  if (c->capturing && c->slab.on)
+    // a slab-decomposed step is replayed from the list build on: k_begin_step and the particle exchange (NCCL transfers
+    // whose sizes the host reads back) stay on the stream, see enqueue_steps
+    rc = build_neighbor_lists(c);
+  else {
+    LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, (c->capturing && fuse_nonpressure_enabled(c)) ? 1 : 0);
+    rc = build_neighbors(c);
+  }
   if (rc) return rc;
   if (!c->capturing) {
     rc = ensure_list_capacity(c);
@@ -1264,7 +1349,9 @@ int launch_step(dfr_context *c) {
   c->vcur = 1 - c->vcur;
   if (!c->slab.p2p) SLAB_SYNC(c, c->vel[c->vcur].p, sizeof(double4));  // peer stores: ordered by the CFL all-reduce below
   if (c->n_dyn_p > 0) LAUNCH(c, k_cfl_boundary, cdiv(c->n_dyn_p, 128), 128, c->dSt.p, c->bvel.p, c->dyn_begin, c->n_dyn_p);
-  if (c->slab.on) {  // max |v + a h|^2 over all slabs (ordered bits of positive doubles)
+  if (c->slab.on && c->slab.mail_ok)  // max |v + a h|^2 over all slabs (ordered bits of positive doubles)
+    LAUNCH(c, k_slab_max_u64, 1, 64, c->dSt.p, c->slab.mail, &c->dSt.p->cfl_max_bits);
+  else if (c->slab.on) {
     rc = slab_allreduce(c, &c->dSt.p->cfl_max_bits, 1, ncclUint64, ncclMax);
     if (rc) return rc;
   }
@@ -1284,8 +1371,12 @@ int launch_step(dfr_context *c) {
   if (c->P.n_bodies > 0) {
     if (c->slab.on) {  // per-body force / torque / Jacobian rows: sum over the slabs, then every rank advances the bodies alike
       LAUNCH(c, k_body_rows_to_buf, c->P.n_bodies, 256, c->dBodies.p, c->acc_rows.p, c->slab.body_buf.p);
-      rc = slab_allreduce(c, c->slab.body_buf.p, (size_t)c->P.n_bodies * ACC_N, ncclDouble, ncclSum);
-      if (rc) return rc;
+      if (c->slab.mail_ok)
+        LAUNCH(c, k_slab_sum_f64, 1, 256, c->dSt.p, c->slab.mail, c->slab.body_buf.p, c->P.n_bodies * ACC_N);
+      else {
+        rc = slab_allreduce(c, c->slab.body_buf.p, (size_t)c->P.n_bodies * ACC_N, ncclDouble, ncclSum);
+        if (rc) return rc;
+      }
       LAUNCH(c, k_body_buf_apply, c->P.n_bodies, 32, c->dBodies.p, c->slab.body_buf.p);
     } else
       LAUNCH(c, k_body_reduce, c->P.n_bodies, 256, c->dBodies.p, c->acc_rows.p);
@@ -1533,6 +1624,9 @@ void dfr_destroy(dfr_context *c) {
   for (int k = 0; k < 2; k++) { c->slab.s_pos[k].free(); c->slab.s_vel[k].free(); c->slab.s_misc[k].free(); }
   for (void *p : c->slab.ipc_opened)
     if (p) cudaIpcCloseMemHandle(p);
+  for (void *p : c->slab.ipc_more)
+    if (p) cudaIpcCloseMemHandle(p);
+  c->slab.seq.free(); c->slab.mbox.free(); c->slab.mflag.free();
   c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free(); c->slab.flags.free(); c->slab.ipc_stage.free();
   if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
   if (c->slab.h_stage) cudaFreeHost(c->slab.h_stage);
@@ -2165,6 +2259,34 @@ int relax_list_capacity(dfr_context *c) {
 }
 int enqueue_steps(dfr_context *c, int n_steps, int gated, StepBatch &B) {
   for (int s = 0; s < n_steps; s++) {
+    if (c->slab.on) {
+      // Every rank must take the same path in the same step (the two paths make different numbers of ghost-update
+      // passes): the choice only depends on things all ranks share.  The head of the step - k_begin_step and the particle
+      // exchange with its two host read-backs - stays on the stream; the rest is one graph replay.
+      if (!graph_stepping_possible(c) || c->fresh_steps > 0) {
+        if (c->fresh_steps > 0) c->fresh_steps--;
+        int rc = launch_step(c);
+        if (rc) return rc;
+        continue;
+      }
+      LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, fuse_nonpressure_enabled(c) ? 1 : 0);
+      int rc = slab_exchange_and_sort(c);  // leaves hSt current
+      if (rc) return rc;
+      dfr_context::StepGraph &sgs = c->step_graph[0][c->cur];
+      if (!sgs.exec) {
+        rc = capture_step_graph(c, 0);
+        if (rc) return rc;  // a rank that fell back alone would hang the others: report instead
+      }
+      if (B.graph_steps == 0) {
+        B.it0 = c->hSt->total_iters;
+        B.itv0 = c->hSt->total_iters_v;
+      }
+      CU(cudaGraphLaunch(sgs.exec, c->stream));
+      c->vcur = 1 - c->vcur;  // the body's velocity-buffer flip (k_nonpressure / k_apply_accel)
+      B.graph_steps++;
+      B.last = &sgs;
+      continue;
+    }
     if (graph_stepping_possible(c) && c->fresh_steps == 0) {
       int rc = relax_list_capacity(c);
       if (rc) return rc;
@@ -2208,6 +2330,10 @@ void account_graph_launches(dfr_context *c, const StepBatch &B, int64_t steps_ex
   if (!B.last) return;
   c->launches += steps_executed * B.last->n_static + (c->hSt->total_iters_v - B.itv0) * B.last->n_div_body +
                  (c->hSt->total_iters - B.it0) * B.last->n_prs_body;
+  if (c->slab.on)  // ghost updates of the replayed steps (32-byte rows; the row count of the last exchange stands for all of them)
+    c->slab.exchanged_bytes += c->slab.sync_rows * 32 * (steps_executed * c->slab.cap_syncs_static +
+                                                         (c->hSt->total_iters_v - B.itv0) * c->slab.cap_syncs_div +
+                                                         (c->hSt->total_iters - B.it0) * c->slab.cap_syncs_prs);
 }
 }  // namespace
 
@@ -2252,7 +2378,7 @@ int dfr_run_trajectory(dfr_context *c, int max_steps, int *steps_done) {
   int s = 0;
   // batches of steps between two looks at `finished`; replayed steps past the end of the trajectory are skipped on the
   // device (IF node), steps on the stream path are enqueued one at a time as before
-  const int batch_max = (graph_stepping_possible(c) && getenv_int("DFR_TRAJECTORY_BATCH") >= 0)
+  const int batch_max = (graph_stepping_possible(c) && !c->slab.on && getenv_int("DFR_TRAJECTORY_BATCH") >= 0)
                             ? std::max(1, getenv_int("DFR_TRAJECTORY_BATCH") ? getenv_int("DFR_TRAJECTORY_BATCH") : 16)
                             : 1;
   while (s < max_steps) {

@@ -150,13 +150,22 @@ __device__ __forceinline__ double4 ld4(const double4 *p) {
 // peer buffer), so that a ghost update costs no extra pass over the data and no collective launch - only a flag.
 // lo / hi are null on a single context or with the NCCL transport.
 // ---------------------------------------------------------------------------------------------
+// The row ranges come from device memory (StepState::slab_ranges, written by k_slab_ranges after every exchange; the low
+// neighbour's own_end arrives in the exchange's count message), so that a recorded step graph stays valid from step to step.
 struct GhostOut {
-  double4 *lo, *hi;  // peer arrays, already offset to the first ghost row that mirrors my boundary layer
-  int lo_begin, lo_end, hi_begin, hi_end;  // my boundary-layer rows
+  double4 *lo, *hi;          // the neighbours' arrays (base addresses)
+  const int *ranges;         // StepState::slab_ranges: [0] own_begin [1] own_end [2] end of my low boundary layer [3] begin of the high one
+  const int *lo_nb_own_end;  // the low neighbour's own_end: its ghost_hi range, which mirrors my low boundary layer, starts there
 };
 __device__ __forceinline__ void ghost_store(const GhostOut &g, int i, const double4 &v) {
-  if (g.lo && i >= g.lo_begin && i < g.lo_end) stg4(g.lo + (i - g.lo_begin), v);
-  if (g.hi && i >= g.hi_begin && i < g.hi_end) stg4(g.hi + (i - g.hi_begin), v);
+  if (g.lo) {
+    const int b = g.ranges[0];
+    if (i >= b && i < g.ranges[2]) stg4(g.lo + *g.lo_nb_own_end + (i - b), v);
+  }
+  if (g.hi) {  // the high neighbour's ghost_lo range starts at 0
+    const int b = g.ranges[3];
+    if (i >= b && i < g.ranges[1]) stg4(g.hi + (i - b), v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1009,6 +1018,8 @@ __global__ void __launch_bounds__(DFR_CTA_THREADS, DFR_RESIDENT(EXTRA == RHO_X_N
 // Slab-decomposed contexts only store the local sum: the rule needs the sum over all slabs (k_solver_decide).
 #define RES_THREADS 256
 #define RES_BLOCKS 16
+template <bool PRESSURE>
+__device__ __forceinline__ void solver_decide(const Params &P, StepState *st, double avg, unsigned long long cond, int policy);
 // cond / policy (graph stepping, else 0): `cond` is the handle of the WHILE node this kernel's iteration body hangs in -
 // it is cleared when the solve closes; policy 1 = this is the divergence solve with the fused non-pressure pass enabled:
 // decide whether the next iteration carries it (the iteration count of the previous step predicts the last iteration;
@@ -1059,7 +1070,12 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual_finish(const __grid_co
     st->res_sum = total;
     return;
   }
-  const double avg = total / (double)nf;
+  solver_decide<PRESSURE>(P, st, total / (double)nf, cond, policy);
+}
+// The stopping rules of pressureSolve / divergenceSolve (TimeStepDiffDFSPH.cpp:711-743, :828-861) on the mean residual of
+// the iteration that just ran; one thread.  cond / policy: see k_residual_finish.
+template <bool PRESSURE>
+__device__ __forceinline__ void solver_decide(const Params &P, StepState *st, double avg, unsigned long long cond, int policy) {
   st->last_residual = avg;
   if (PRESSURE) {
     const double eta = P.max_error * 0.01 * P.density0;

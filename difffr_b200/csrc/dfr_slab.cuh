@@ -125,25 +125,108 @@ __global__ void k_slab_ranges(const __grid_constant__ Params P, const SlabGeom G
 }
 
 // TimeStepDiffDFSPH::pressureSolve / divergenceSolve stopping rules (:711-743, :828-861) on the all-reduced residual
+// (NCCL transport: the sum over the slabs arrives in st->res_sum)
 template <bool PRESSURE>
 __global__ void k_solver_decide(const __grid_constant__ Params P, StepState *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (!(PRESSURE ? st->prs_active : st->div_active)) return;
-  const double avg = st->res_sum / (double)P.n_global;
-  st->last_residual = avg;
-  if (PRESSURE) {
-    const double eta = P.max_error * 0.01 * P.density0;
-    const int it = st->prs_iters + 1;
-    st->prs_iters = it;
-    const bool chk = (avg <= eta);
-    if (!((!chk || it < P.min_iter) && it < P.max_iter)) st->prs_active = 0;
-  } else {
-    const double eta = (1.0 / st->h_step) * P.max_error_v * 0.01 * P.density0;
-    const int it = st->div_iters + 1;
-    st->div_iters = it;
-    const bool chk = (avg <= eta);
-    if (!((!chk || it < 1) && it < P.max_iter_v)) st->div_active = 0;
+  solver_decide<PRESSURE>(P, st, st->res_sum / (double)P.n_global, 0ull, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small all-reduces over peer memory.  Every rank maps every rank's mailbox (cudaIpc) and writes its contribution
+// straight into all of them over NVLink; a rank then finds the n contributions in its own mailbox and combines them in
+// rank order, so that every rank computes the same bits.  One block, no collective library, no host: the call sits in
+// the stream (or in a recorded step graph) like any other kernel.  Sequence numbers make the two payload slots safe: a
+// rank can only write its contribution to all-reduce q + 2 into the slot of q after it has finished q + 1, which needs
+// every peer's contribution to q + 1, which a peer only sends after it has read q.
+// ---------------------------------------------------------------------------------------------
+#define DFR_MAX_SLABS 16
+struct SlabMail {
+  double *box[DFR_MAX_SLABS];               // rank r's mailbox: [2 slots][n ranks][cap] doubles
+  unsigned long long *flag[DFR_MAX_SLABS];  // rank r's flags: [n ranks], the sequence number rank k has delivered
+  unsigned long long *seq;                  // my count of all-reduces so far; never reset (the peers' flags are not either)
+  int n, rank, cap;
+};
+enum { MAIL_SUM_F64 = 0, MAIL_MAX_U64 = 1 };
+// data[0..count) <- combination over all ranks; called by every thread of one block
+template <int OP>
+__device__ __forceinline__ void mailbox_allreduce(const SlabMail &M, StepState *st, double *data, int count, unsigned long long timeout_ns) {
+  __shared__ unsigned long long seq_s;
+  __shared__ int fail_s;
+  if (threadIdx.x == 0) {
+    seq_s = ++(*M.seq);
+    fail_s = 0;
   }
+  __syncthreads();
+  const unsigned long long q = seq_s;
+  const size_t slot = (size_t)(q & 1ull) * (size_t)M.n * (size_t)M.cap;
+  if (count > M.cap) count = M.cap;
+  for (int p = 0; p < M.n; p++) {
+    double *dst = M.box[p] + slot + (size_t)M.rank * (size_t)M.cap;
+    for (int k = threadIdx.x; k < count; k += blockDim.x) dst[k] = data[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < M.n) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(M.flag[threadIdx.x] + M.rank), "l"(q) : "memory");
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long *mine = M.flag[M.rank] + threadIdx.x;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= q) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        fail_s = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (fail_s) {
+    if (threadIdx.x == 0) atomicOr(&st->error_flags, 32);
+    return;
+  }
+  const double *in = M.box[M.rank] + slot;
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    if (OP == MAIL_SUM_F64) {
+      double s = 0.0;
+      for (int r = 0; r < M.n; r++) s += __ldcv(in + (size_t)r * M.cap + k);  // volatile loads: the peers wrote these lines
+      data[k] = s;
+    } else {
+      unsigned long long m = 0ull;
+      for (int r = 0; r < M.n; r++) m = max(m, (unsigned long long)__double_as_longlong(__ldcv(in + (size_t)r * M.cap + k)));
+      data[k] = __longlong_as_double((long long)m);
+    }
+  }
+  __syncthreads();
+}
+#define MAIL_TIMEOUT_NS 5000000000ull
+// the residual of a Jacobi iteration summed over the slabs + the stopping rule (replaces ncclAllReduce + k_solver_decide)
+template <bool PRESSURE>
+__global__ void __launch_bounds__(64) k_slab_residual_decide(const __grid_constant__ Params P, StepState *st, const SlabMail M,
+                                                             unsigned long long cond, int policy) {
+  if (!(PRESSURE ? st->prs_active : st->div_active)) {
+    if (cond && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0u);
+    return;
+  }
+  mailbox_allreduce<MAIL_SUM_F64>(M, st, &st->res_sum, 1, MAIL_TIMEOUT_NS);
+  if (threadIdx.x != 0) return;
+  if (st->error_flags & 32) {  // a peer did not answer: close the solve, the host reports the error
+    if (PRESSURE) st->prs_active = 0; else st->div_active = 0;
+    if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0u);
+    return;
+  }
+  solver_decide<PRESSURE>(P, st, st->res_sum / (double)P.n_global, cond, policy);
+}
+// max |v + a h|^2 over the slabs (ordered bits of positive doubles)
+__global__ void __launch_bounds__(64) k_slab_max_u64(StepState *st, const SlabMail M, unsigned long long *value) {
+  mailbox_allreduce<MAIL_MAX_U64>(M, st, reinterpret_cast<double *>(value), 1, MAIL_TIMEOUT_NS);
+}
+// the per-body force / torque / Jacobian rows summed over the slabs
+__global__ void __launch_bounds__(256) k_slab_sum_f64(StepState *st, const SlabMail M, double *buf, int count) {
+  mailbox_allreduce<MAIL_SUM_F64>(M, st, buf, count, MAIL_TIMEOUT_NS);
 }
 
 // Peer-memory transport: "my boundary rows of this pass are in your ghost range" / "are yours in mine?".
@@ -151,8 +234,11 @@ __global__ void k_solver_decide(const __grid_constant__ Params P, StepState *st)
 // flags[0] is written by the low neighbour, flags[1] by the high one.  A wait that lasts longer than `timeout_ns` gives
 // up and raises error bit 32 (a peer that failed must not hang this GPU).
 __global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, volatile unsigned long long *my_flags,
-                                   unsigned long long value, unsigned long long timeout_ns, int *error_flags) {
+                                   unsigned long long *pass_counter, unsigned long long timeout_ns, int *error_flags) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // the pass number lives on the device (both neighbours make the same sequence of calls; never reset, like the flags),
+  // so that the kernel can be part of a recorded step graph
+  const unsigned long long value = ++(*pass_counter);
   __threadfence_system();
   if (peer_lo_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_lo_flag), "l"(value) : "memory");
   if (peer_hi_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_hi_flag), "l"(value) : "memory");

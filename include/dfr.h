@@ -179,7 +179,11 @@ int dfr_set_gradient_mode(dfr_context *ctx, int mode);
  * the body records the getters read.  The stream path (speculated batches of iterations, one read-back per solve) is
  * used instead: in the first four steps after finalize / reset / load (the neighbour-list capacities are being
  * watched), with the rigid contact solver once every 500 steps (the reference's z-sort of the contact order runs on the
- * host), while per-kernel profiling is on, on slab-decomposed contexts, and with DFR_NO_GRAPH=1. */
+ * host), while per-kernel profiling is on, and with DFR_NO_GRAPH=1.
+ * Slab-decomposed contexts (peer-memory transport): k_begin_step and the particle exchange - NCCL transfers whose sizes the
+ * host reads back, two synchronisations - stay on the stream, everything from the list build on is one graph replay per
+ * step; residual sums, the CFL maximum and the per-body rows are all-reduced by small kernels over peer-mapped mailboxes
+ * (no collective calls inside the solves).  With DFR_SLAB_TRANSPORT=nccl the round-1 stream path is used. */
 int dfr_step(dfr_context *ctx, int n_steps);
 
 /* Runs steps until TimeStepDiffDFSPH::is_trajectory_finish_callback() would be true
