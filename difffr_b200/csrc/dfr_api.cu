@@ -1326,6 +1326,10 @@ int launch_step(dfr_context *c) {
     if (rc) return rc;
     scale_kv = c->cfg.use_divergence_warmstart != 0;
   }
+  // reaction of the boundary viscosity on dynamic bodies (force, torque, dF/dv), from the velocities the non-pressure pass sees
+  if (c->cfg.viscosity_method == 1 && c->cfg.viscosity_boundary != 0.0 && c->n_acc_blocks > 0)
+    LAUNCH(c, k_boundary_viscosity, c->n_acc_blocks, BS_WARPS * 32, c->P, c->dSt.p, c->dBodies.p, c->blk_body.p, c->blk_first.p, c->xrho.p,
+           c->vel[c->vcur].p, c->bpos.p, c->bvel.p, c->dyn_begin, c->off_d.p, c->idx_d.p, c->acc_rows.p);
   if (c->cfg.surface_tension_method == 2 && !fuse_normals)
   {
     PLAUNCH(c, k_normals, g, c->P, c->dSt.p, c->xrho.p, list_f(c), c->normal.p, ghost_out(c, GA_NORMAL));
@@ -1470,6 +1474,7 @@ int reset_device_state(dfr_context *c) {
   st.own_begin = 0;
   st.own_end = st.nf;
   st.spec_div = 1;
+  st.spec_div_prev = 1;
   st.div_streak = 2;
   if (c->slab.on) {
     c->slab.h_ranges[0] = 0;
@@ -1822,14 +1827,6 @@ int dfr_finalize(dfr_context *c) {
   P.target_time = cfg.target_time; P.uniform_acc_time = cfg.uniform_acc_rb_time;
   P.time_step_size0 = cfg.time_step_size;
   P.n_bodies = (int)c->bodies.size();
-  // Viscosity_Standard::step (Viscosity_Standard.cpp:273-300) applies the boundary-viscosity reaction force (and, with
-  // BACKWARD, its Jacobian) to the neighbouring body; this path only applies the acceleration to the fluid, which is the
-  // whole effect for static bodies but would silently break momentum exchange and sensitivities of a dynamic one
-  if (cfg.viscosity_boundary != 0.0 && cfg.viscosity_method == 1)
-    for (const auto &hb : c->bodies)
-      if (hb.dynamic)
-        return fail(c, DFR_ERR_INVALID, "viscosityBoundary != 0 with a dynamic rigid body: the reaction force on the body is not on this path");
-
   // ---- boundary layout: static bodies first, then dynamic ----
   int off = 0;
   std::vector<int> order;

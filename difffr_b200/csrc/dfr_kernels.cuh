@@ -1093,11 +1093,14 @@ __device__ __forceinline__ void solver_decide(const Params &P, StepState *st, do
     const bool go_on = (!chk || it < 1) && it < P.max_iter_v;
     if (!go_on) st->div_active = 0;
     if (policy == 1) {
+      // the fused pass rides on every iteration from min(iterations of the last two steps) on: a pass that turns out not
+      // to be the last costs ~0.6 of a plain pass, a missing one the whole stand-alone k_nonpressure (~2.6 plain passes)
       if (go_on)
-        st->fuse_now = ((it + 1 == st->spec_div && st->div_streak >= 2) || it + 1 > st->spec_div) ? 1 : 0;
+        st->fuse_now = (it + 1 >= min(st->spec_div, st->spec_div_prev)) ? 1 : 0;
       else {
         st->np_done = st->fuse_now;  // the pass of this (last) iteration carried the non-pressure accelerations
         st->div_streak = (it == st->spec_div) ? min(st->div_streak + 1, 1000) : 0;
+        st->spec_div_prev = st->spec_div;
         st->spec_div = max(it, 1);
       }
     }
@@ -1360,6 +1363,92 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_side(const __grid_co
 #pragma unroll
     for (int w2 = 0; w2 < BS_WARPS; w2++) s += rows[w2][k];
     acc_rows[(size_t)blockIdx.x * ACC_N + k] += s;
+  }
+}
+
+// Reaction of the boundary-viscosity term on dynamic bodies (Viscosity_Standard::step, Viscosity_Standard.cpp:273-318):
+// a fluid particle i next to boundary particle j gets the acceleration a_ij (k_nonpressure / the fused pass), the body
+// gets -m_i a_ij at x_j (BoundaryModel::addForce) and, with BACKWARD defined as the reference builds it, the Jacobian
+// -m_i (d a_ij / d v_j + dt d a_ij / d x_j) is added to the particle's dF/dv array (only that one).  Gathered from the
+// boundary side like the pressure forces: same blocks, same accumulator rows as k_boundary_side.  Runs after the
+// divergence solve (the velocities the non-pressure pass sees) with dt = the step's old time step size.
+__global__ void __launch_bounds__(BS_WARPS * 32) k_boundary_viscosity(const __grid_constant__ Params P, const StepState *st, const BodyDev *bodies,
+                                                                       const int *blk_body, const int *blk_first, const double4 *xrho,
+                                                                       const double4 *vel, const double4 *bpos, const double4 *bvel, int dyn_begin,
+                                                                       const unsigned int *off_d, const int *idx_d, double *acc_rows) {
+  __shared__ double rows[BS_WARPS][ACC_N];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = lane; k < ACC_N; k += 32) rows[wid][k] = 0.0;
+  __syncwarp();
+  const BodyDev &B = bodies[blk_body[blockIdx.x]];
+  const double dt = st->h_step;
+  const double h2s = P.support_radius * P.support_radius;
+  const int first = blk_first[blockIdx.x];
+  const int last = min(first + BS_PART_PER_BLOCK, B.p_begin + B.p_count);
+  for (int bj = first + wid; bj < last; bj += BS_WARPS) {
+    const double4 pj = bpos[bj];
+    const double4 vj4 = bvel[bj];
+    const double factor = 10.0 * P.viscosity_b * P.density0 * pj.w;
+    const int t = bj - dyn_begin;
+    const int s = (int)off_d[t], e = (int)off_d[t + 1];
+    d3 sF = mk3(0, 0, 0);
+    double sJ[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) sJ[k] = 0.0;
+    for (int p = s + lane; p < e; p += 32) {
+      const int i = idx_d[p];
+      if (i < st->own_begin || i >= st->own_end) continue;  // ghosts are summed by the slab that owns them
+      const double4 pi = ldg4(xrho + i);  // (x_i, rho_i)
+      const double4 vi4 = ldg4(vel + i);
+      const d3 r = mk3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      const d3 dv = mk3(vi4.x - vj4.x, vi4.y - vj4.y, vi4.z - vj4.z);
+      d3 gW;
+      m33 H;
+      cubic_grad_gradgrad(P, r, gW, H);
+      const double n = dot(r, r) + 0.01 * h2s;
+      const double tmp1 = dot(dv, r) / n;
+      const d3 a = (factor / pi.w * tmp1) * gW;
+      sF -= P.mass * a;
+      // grad1..4 of :283-293, grad_a_to_vj of :303
+      const m33 g1 = outer((-1.0 / pi.w * tmp1) * gW, (-1.0) * gW);
+      const m33 g2 = outer((1.0 / n) * gW, (-1.0) * dv);
+      const m33 g3 = outer((-dot(dv, r) / (n * n) * 2.0) * gW, (-1.0) * r);
+      const m33 g_a_v = outer((-factor / pi.w / n) * gW, r);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const double g_a_x = factor / pi.w * (g1.a[k] + g2.a[k] + g3.a[k] - tmp1 * H.a[k]);
+        sJ[k] += -P.mass * (g_a_v.a[k] + dt * g_a_x);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sF.x += __shfl_xor_sync(DFR_FULL, sF.x, o);
+      sF.y += __shfl_xor_sync(DFR_FULL, sF.y, o);
+      sF.z += __shfl_xor_sync(DFR_FULL, sF.z, o);
+#pragma unroll
+      for (int k = 0; k < 9; k++) sJ[k] += __shfl_xor_sync(DFR_FULL, sJ[k], o);
+    }
+    if (lane == 0) {
+      double *row = rows[wid];
+      const d3 rj = mk3(pj.x, pj.y, pj.z) - B.pos;
+      const d3 tq = cross(rj, sF);
+      row[ACC_F + 0] += sF.x;
+      row[ACC_F + 1] += sF.y;
+      row[ACC_F + 2] += sF.z;
+      row[ACC_T + 0] += tq.x;
+      row[ACC_T + 1] += tq.y;
+      row[ACC_T + 2] += tq.z;
+#pragma unroll
+      for (int k = 0; k < 9; k++) row[ACC_FV + k] += sJ[k];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < ACC_N; k += BS_WARPS * 32) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < BS_WARPS; w2++) s2 += rows[w2][k];
+    acc_rows[(size_t)blockIdx.x * ACC_N + k] += s2;
   }
 }
 

@@ -13,7 +13,7 @@ __global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, Bo
     st->step_count += 1;
     // graph stepping (fuse_mode 1): does the first divergence iteration carry the non-pressure pass?
     st->np_done = 0;
-    st->fuse_now = (fuse_mode == 1 && st->spec_div <= 1 && st->div_streak >= 2) ? 1 : 0;
+    st->fuse_now = (fuse_mode == 1 && min(st->spec_div, st->spec_div_prev) <= 1) ? 1 : 0;
     st->h_step = st->h;  // "const Real h = tm->getTimeStepSize()" at :535
     st->div_active = 1;
     st->div_iters = 0;

@@ -67,6 +67,7 @@ struct StepState {
   // CUDA-graph stepping (dfr_api.cu: StepGraph): the solver loops are WHILE nodes, so what the host used to decide
   // between speculated batches is decided here
   int spec_div, div_streak;         // divergence iterations of the previous step / consecutive steps that matched the prediction
+  int spec_div_prev;                // ... and of the step before that
   int fuse_now;                     // the next divergence iteration's k_rho also evaluates the non-pressure accelerations
   int np_done;                      // ... and that pass was the last active iteration: k_apply_accel instead of k_nonpressure
 };

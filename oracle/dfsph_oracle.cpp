@@ -996,8 +996,25 @@ void viscosityStandard(dfr_context *c) {
           const Vec3 acc = (d * mub * (density0 * bm.V[j] / density_i) * dot(vi - vj, xixj) / (sqnorm(xixj) + 0.01 * h2)) * c->K.gradW(xi - xj);
           ai += acc;
           bm.addForce(xj, -c->mass * acc, tid());
-          // The reference also adds a viscosity Jacobian to grad_force_to_v here (:275-318); it is
-          // unreachable in every shipped scene (mu_b = 0) and is not restated.
+          // ===== backward (Viscosity_Standard.cpp:275-318; BACKWARD is defined at :12) =====
+          if (bm.dynamic) {
+            const double factor = d * mub * density0 * bm.V[j];
+            const double n = sqnorm(xixj) + 0.01 * h2;
+            const double tmp1 = dot(vi - vj, xixj) / n;
+            const Vec3 gW = c->K.gradW(xi - xj);
+            const Vec3 tmp2 = tmp1 * gW;
+            const Mat3 grad1 = (-1.0 / density_i) * outer(tmp2, (-1.0) * gW);                  // grad density_i
+            const Mat3 grad2 = (1.0 / n) * outer(gW, (-1.0) * (vi - vj));                      // grad xixj
+            const Mat3 grad3 = (-dot(vi - vj, xixj) / (n * n) * 2.0) * outer(gW, (-1.0) * xixj);  // grad xixj.squaredNorm
+            const Mat3 grad4 = tmp1 * ((-1.0) * c->K.gradGradW(xi - xj));
+            const Mat3 grad_a_to_xj = (factor / density_i) * (grad1 + grad2 + grad3 + grad4);
+            const Mat3 grad_a_to_vj = (-factor / density_i / n) * outer(gW, xixj);
+            const double dt = c->h;  // TimeManager::getTimeStepSize() at this point of the step: the old step size
+            const Mat3 grad_force_to_vj = (-c->mass) * (grad_a_to_vj + dt * grad_a_to_xj);
+            // (the reference adds to the particle's array from inside its parallel loop over i; serialised here)
+#pragma omp critical(visc_b_grad)
+            bm.g_force_v[j] += grad_force_to_vj;
+          }
         }
       }
     }

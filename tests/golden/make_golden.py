@@ -29,6 +29,12 @@ CASES = {
                           dict(steps=8, init_v=(0.8, -0.5, 0.1), init_omega=(1.0, 2.0, -0.5), load_state=True)),
     "cfl_iter_nowarm_nogyro": (dict(n_target=1200, n_boxes=1), dict(cfl_method=2, use_pressure_warmstart=0, use_divergence_warmstart=0, rigid_body_mode=1,
                                                                     gradient_mode=2, max_error=0.05, target_time=0.05), dict(steps=6)),
+    # boundary viscosity (Viscosity_Standard.cpp:273-318): acceleration of the fluid, reaction force / torque on the body and
+    # the dF/dv Jacobian contribution; no shipped scene sets it, the reference's code path is live all the same
+    "boundary_viscosity_1box": (dict(n_target=1500, n_boxes=1, jitter=0.2, seed=5), dict(surface_tension_method=2, surface_tension=0.2, max_error=0.05,
+                                                                                           target_time=0.05, viscosity=0.02, viscosity_boundary=0.3,
+                                                                                           gradient_mode=0), dict(steps=6, init_v=(0.6, -0.4, 0.2),
+                                                                                                                  init_omega=(1.0, -2.0, 0.5))),
     # penalty rigid-rigid contact + friction + manager (BASELINE.json configs[2]); reset() after step 4 exercises the
     # history-dependent contact order of the reference (oracle/oracle_contact.inc)
     "contact_manager_2box": (dict(n_target=1500), dict(surface_tension_method=2, surface_tension=0.3, max_error=0.05, target_time=0.05,
