@@ -676,7 +676,14 @@ def main():
     ncu = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(ncu):
         try:
-            roofline["traffic"] = json.load(open(ncu)).get(top_name)
+            prof_file = json.load(open(ncu))
+            roofline["traffic"] = prof_file.get(top_name)
+            # what actually bounds the list kernels on this part: the SM's L1 data stage (ncu, not measured in this run)
+            busy = prof_file.get("l1_data_stage_busy", {}).get(top_name)
+            if busy is not None:
+                roofline["binding_resource"] = {"name": "L1 data-stage wavefronts (l1tex__data_pipe_lsu_wavefronts, share of peak)",
+                                                "busy_frac": busy, "source": "profiles/traffic.json from the ncu --set full capture "
+                                                "summarised in profiles/r2_ncu_full.md; see profiles/r2_gather_analysis.md"}
         except Exception:
             pass
 

@@ -644,10 +644,22 @@ __global__ void __launch_bounds__(DFR_CTA_THREADS) k_nbr_build(const __grid_cons
     const int lane = i & 31;
     const double4 p = pos[i];
     (void)lane;
+    // four indices are collected in registers and leave as one 16-byte store (the ELL-4 group of this lane): a quarter of
+    // the store instructions of the scalar version, each a full group instead of a 4-byte piece of it
+    int4 pend = make_int4(0, 0, 0, 0);
+    int4 *row_f = reinterpret_cast<int4 *>(idx_f) + ((size_t)(i >> 5) * (size_t)(cap_f >> 2)) * 32 + (i & 31);
     for_each_in_range(P, gf, p.x, p.y, p.z, i, [&](int j) {
-      if (cf < cap_f) idx_f[nbr_slot(cap_f, i, cf)] = j;
+      const int k = cf & 3;
+      if (k == 0) pend.x = j;
+      else if (k == 1) pend.y = j;
+      else if (k == 2) pend.z = j;
+      else {
+        pend.w = j;
+        if (cf < cap_f) row_f[(size_t)(cf >> 2) * 32] = pend;
+      }
       cf++;
     });
+    if ((cf & 3) != 0 && cf < cap_f) row_f[(size_t)(cf >> 2) * 32] = pend;  // the last, partly filled group
     int ocx, ocy, ocz;
     cell_of(P.grid, p.x, p.y, p.z, ocx, ocy, ocz);
     const int own_cell = cell_lin(P.grid, ocx, ocy, ocz);

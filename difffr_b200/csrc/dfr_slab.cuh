@@ -156,7 +156,7 @@ __device__ __forceinline__ void mailbox_allreduce(const SlabMail &M, StepState *
   __shared__ int fail_s;
   if (threadIdx.x == 0) {
     seq_s = ++(*M.seq);
-    fail_s = 0;
+    fail_s = (st->error_flags & 32) ? 1 : 0;  // a peer already failed to answer once: do not stack further time-outs
   }
   __syncthreads();
   const unsigned long long q = seq_s;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void mailbox_allreduce(const SlabMail &M, StepState *
     unsigned long long t0, t1, v;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     const unsigned long long *mine = M.flag[M.rank] + threadIdx.x;
-    for (;;) {
+    while (!fail_s) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
       if (v >= q) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -239,6 +239,7 @@ __global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned lo
   // the pass number lives on the device (both neighbours make the same sequence of calls; never reset, like the flags),
   // so that the kernel can be part of a recorded step graph
   const unsigned long long value = ++(*pass_counter);
+  if (*error_flags & 32) return;  // a neighbour already failed to answer once: do not stack further time-outs
   __threadfence_system();
   if (peer_lo_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_lo_flag), "l"(value) : "memory");
   if (peer_hi_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_hi_flag), "l"(value) : "memory");

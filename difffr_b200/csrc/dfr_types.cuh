@@ -142,6 +142,20 @@ __device__ __forceinline__ size_t nbr_slot(int cap, int i, int k) {
 // load(j) -> payload gathered for neighbour j; use(payload, j) accumulates it.  Neighbours are consumed in slot
 // order, so sums have the same order as a plain sequential loop.  Slots past the row's count are replaced by the
 // always-valid index `safe` for the (discarded) gather.
+// One ELL-4 group of a row.  DFR_LIST_NOALLOC=1 (tuning build): the index stream does not allocate in L1, so that it
+// cannot evict the gathered records the warps of the SM share.
+#ifndef DFR_LIST_NOALLOC
+#define DFR_LIST_NOALLOC 0
+#endif
+__device__ __forceinline__ int4 ld_list4(const int4 *p) {
+#if DFR_LIST_NOALLOC
+  int4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
 template <int U = 4, class Load, class Use>
 __device__ __forceinline__ void for_neighbors4(const NbrList &l, int i, int safe, Load load, Use use) {
   static_assert(U == 1 || U == 2 || U == 4, "sub-batch of the int4 group");
@@ -149,10 +163,10 @@ __device__ __forceinline__ void for_neighbors4(const NbrList &l, int i, int safe
   if (n <= 0) return;
   const int4 *row = reinterpret_cast<const int4 *>(l.idx) + ((size_t)(i >> 5) * (size_t)(l.cap >> 2)) * 32 + (i & 31);
   const int nb = (n + 3) >> 2;
-  int4 jn = __ldg(row);
+  int4 jn = ld_list4(row);
   for (int b = 0; b < nb; b++) {
     const int4 j4 = jn;
-    if (b + 1 < nb) jn = __ldg(row + (size_t)(b + 1) * 32);
+    if (b + 1 < nb) jn = ld_list4(row + (size_t)(b + 1) * 32);
     const int k0 = b << 2;
     int j[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll

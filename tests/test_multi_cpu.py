@@ -102,3 +102,21 @@ def test_slab_plan_balances_and_refuses_thin_slabs():
     z2 = np.concatenate([rng.uniform(0.0, 0.2, 40000), rng.uniform(0.2, 1.0, 10000)])
     planes = cabi.slab_plan(z2, 0.0, cell, 100, 2, 2)
     assert planes[1] < 20
+
+
+def test_population_with_concurrent_contexts_on_the_oracle(oracle_lib):
+    """run_population(concurrency=k): k contexts driven by k host threads give the serial results in candidate order (the
+    thread pool / work queue is backend independent; on the GPU the contexts' kernels overlap, tests/test_rollouts_gpu.py)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from difffr_b200 import rollouts
+
+    serial, steps1 = rollouts.run_population(_oracle_context, CANDIDATES, body=1)
+    stats = {}
+    conc, steps2 = rollouts.run_population(_oracle_context, CANDIDATES, body=1, concurrency=3, stats=stats)
+    assert np.array_equal(steps1, steps2)
+    assert np.array_equal(serial, conc)
+    assert "kernel_launches" in stats
+    # contexts handed in by the caller; more contexts than candidates are not used
+    ctxs = [_oracle_context() for _ in range(2)]
+    again, _ = rollouts.run_population(None, CANDIDATES[:1], body=1, contexts=ctxs)
+    assert np.array_equal(again, serial[:1])

@@ -61,13 +61,17 @@ def loss_gradient(state, grads, target_x):
     return np.concatenate([gx_v0.T @ gx, gx_w0.T @ gx])
 
 
-def test_stone_skipping_whole_trajectory(gpu_factory):
-    path = os.path.join(TRAJ, "traj_stone_skipping.npz")
-    if not os.path.exists(path):
+@pytest.mark.parametrize("name", ["stone_skipping", "water_rafting"])
+def test_whole_trajectory(gpu_factory, name):
+    """stone_skipping: see the module docstring.  water_rafting (BASELINE.json configs[1], diff-water-rafting-bunny.json,
+    105,154 particles, T = 2 s): the bunny floats from the first step, so the runs start to differ at rounding level at
+    once and the envelope applies throughout."""
+    path = os.path.join(TRAJ, f"traj_{name}.npz")
+    if not (os.path.exists(path) and os.path.exists(os.path.join(TRAJ, f"{name}_cpu_drift.npz"))):
         pytest.skip("trajectory record not generated")
     g = np.load(path)
-    drift = np.load(os.path.join(TRAJ, "stone_skipping_cpu_drift.npz"))
-    x0 = np.load(os.path.join(TRAJ, "stone_skipping_settled.npz"))["x"].astype(np.float64)
+    drift = np.load(os.path.join(TRAJ, f"{name}_cpu_drift.npz"))
+    x0 = np.load(os.path.join(TRAJ, f"{name}_settled.npz"))["x"].astype(np.float64)
     assert x0.shape[0] == int(g["n_fluid"])
     ctx = build_gpu(gpu_factory, g, x0)
     b = int(g["dyn_body"])
@@ -80,7 +84,8 @@ def test_stone_skipping_whole_trajectory(gpu_factory):
     cpu_grad_steps = [int(v) for v in drift["grad_steps"]]
     cpu_grad = np.maximum.accumulate(drift["grad_err"][:, :8], axis=0)     # sensitivity blocks 0..7 at the checkpoints
     contact = int(np.argmax(drift["state_err"].max(axis=1) > 1e-9))        # first step (0-based) at which two CPU runs differ at all
-    assert contact > 100
+    if name == "stone_skipping":
+        assert contact > 100
 
     def state_bound(s):
         return STATE_TOL if s < contact else STATE_TOL + ENVELOPE * cpu_state[min(s, len(cpu_state) - 1)]
@@ -127,10 +132,10 @@ def test_stone_skipping_whole_trajectory(gpu_factory):
     assert info.trajectory_finished
     gg = np.array([np.pad(ctx.body_grad(b, w).ravel(), (0, 12))[:12] for w in range(16)])
     end_ref_state, end_ref_grads = ref_state[-1], g["body_grads"][-1]
-    target = np.array([1.7, 1.6, 0.0])  # targetX of the stone in diff-stone-skipping.json
+    target = g["target_x"] if "target_x" in g.files else np.array([1.7, 1.6, 0.0])  # targetX of the scene file
     lg, lr = loss_gradient(got, gg, target), loss_gradient(end_ref_state, end_ref_grads, target)
     out = {
-        "scene": "diff-stone-skipping.json + settled fluid (tests/golden/trajectory/stone_skipping_settled.npz)",
+        "scene": f"{name}: the reference's scene file + settled fluid (tests/golden/trajectory/{name}_settled.npz)",
         "steps_gpu": s, "steps_reference": int(n_ref), "steps_cpu_oracle": int(drift["steps_oracle"]),
         "first_step_at_which_two_cpu_implementations_differ": contact + 1,
         "worst_state_rel_err_before_that": worst_before, "worst_sensitivity_rel_err_before_that": worst_grad_before,
@@ -147,7 +152,7 @@ def test_stone_skipping_whole_trajectory(gpu_factory):
         "state_err_every_25_steps (gpu vs reference | running max of cpu oracle vs reference)": err_curve,
     }
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "trajectory_stone_skipping.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"trajectory_{name}.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps({k: out[k] for k in ("steps_gpu", "steps_reference", "first_step_at_which_two_cpu_implementations_differ",
                                           "worst_state_rel_err_before_that", "worst_sensitivity_rel_err_before_that",

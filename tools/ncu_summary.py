@@ -19,6 +19,7 @@ M = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("
 idx = [(hdr.index(m), lab) for m, lab in M if m in hdr]
 ik = hdr.index("Kernel Name")
 traffic = {}
+l1busy = {}
 with open(out, "w") as f:
     f.write(f"# {title}\n\n`ncu --set full --clock-control none --import-source on` (1x B200, under gpurun); read with `ncu -i ... --page raw --csv`.\n\n")
     f.write("| kernel | " + " | ".join(l for _, l in idx) + " |\n|---|" + "---:|" * len(idx) + "\n")
@@ -42,8 +43,12 @@ with open(out, "w") as f:
                 return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
             base = name.split("<")[0]
             traffic.setdefault(base, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+            l1busy.setdefault(base, []).append(float(r[hdr.index("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")].replace(",", "")) / 100.0)
         except Exception:
             pass
 print(open(out).read())
 if len(sys.argv) > 4:
-    json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(sys.argv[4], "w"), indent=1)
+    d = {k: sum(v) / len(v) for k, v in traffic.items()}
+    # busiest unit of the list kernels: the L1 data stage (share of its peak wavefront rate, mean over the profiled launches)
+    d["l1_data_stage_busy"] = {k: sum(v) / len(v) for k, v in l1busy.items()}
+    json.dump(d, open(sys.argv[4], "w"), indent=1)
