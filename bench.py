@@ -248,7 +248,8 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, mode="slab"):
+def workload_config(n_gpus, mode="slab", per_gpu=None):
+    N_PARTICLES = per_gpu or globals()["N_PARTICLES"]
     l2 = "working set per step (~0.5 GB of particle state and neighbour lists per GPU) exceeds the 126 MB L2; no flush needed"
     if n_gpus > 1 and mode == "slab":
         return {"workload": f"synthetic dam break + {N_BOXES} dynamic rigid boxes, ONE scene of {n_gpus} x {N_PARTICLES} fluid particles "
@@ -736,7 +737,7 @@ def main():
         "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world, args.mode),
+        "config": workload_config(world, args.mode, args.particles),
         "wall_ms_per_step": wall_ms / args.steps,
         "solver": {"mean_neighbors": nbar, "divergence_iters": D, "pressure_iters": P, "h": i1.time_step_size},
         "clocks": clocks,
