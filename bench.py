@@ -81,16 +81,24 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.window = None
+
+    def mark_begin(self):
+        """The sampler is started well before the timed region (nvidia-smi needs ~0.1 s to come up); only the samples taken
+        between mark_begin() and stop() count."""
+        import datetime
+
+        self.window = datetime.datetime.now()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -104,17 +112,36 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        import datetime
+
+        t_end = datetime.datetime.now()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        out = self._summarise(t_end, filtered=True)
+        if not out["samples"]:  # the region was shorter than one sampling interval: fall back to every sample taken
+            out = self._summarise(t_end, filtered=False)
+            out["note"] = "no sample fell inside the timed region; all samples of the run (warm-up included) are used"
+        return out
+
+    def _summarise(self, t_end, filtered):
+        import datetime
+
         sm, mx, reasons, power = [], [], set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
+            if filtered and self.window is not None and len(f) >= 10:  # keep the samples of the timed region
+                try:
+                    ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f")
+                    if ts < self.window or ts > t_end:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
@@ -517,14 +544,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps ----
-    ctx.step(args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    ctx.step(args.warmup)
+    barrier()
     ms0, l0 = ctx.device_time_ms()
     i0 = ctx.step_info()
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     ctx.step(args.steps)  # one dfr_step call: K steps enqueued back to back, events on the context's stream
     barrier()

@@ -177,6 +177,7 @@ def drift(name):
                         end_state_err=np.array([rel(eo[sl], er[sl]) for sl in sl4]), end_loss_gradient_err=rel(lg(eo, go), lg(er, gr)),
                         end_loss_gradient_oracle=lg(eo, go), end_loss_gradient_reference=lg(er, gr),
                         end_sensitivity_err=np.array([rel(go[w], gr[w]) for w in range(16)]),
+                        iteration_mismatch_steps=int(np.sum((o["step_iters"][:n] != r["step_iters"][:n]) | (o["step_iters_v"][:n] != r["step_iters_v"][:n]))),
                         note="the CPU oracle port against the reference's own code on the same trajectory: how far two FP64 "
                              "implementations of the same algorithm drift apart")
 
