@@ -16,7 +16,7 @@ What is asserted:
     history with the reference's discontinuous rules - the < 20 neighbours cut of the density change, the rho* > 1 gate,
     pairs at distance == support radius), and from then on they are two samples of a chaotic splash: the reference and
     the oracle port end 1.0e-2 apart in position and 1.3e-2 in the loss gradient, with identical iteration counts in
-    every step.  The north-star's "end-of-trajectory loss gradients within 1e-4" is therefore not a property this scene
+    every step (the CUDA path: 0.5e-2 and 1.1e-2).  The north-star's "end-of-trajectory loss gradients within 1e-4" is therefore not a property this scene
     has even between two CPU implementations; the test states the measured numbers
     (gpurun_out/trajectory_stone_skipping.json, copy under profiles/).
 """
