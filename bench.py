@@ -400,15 +400,42 @@ def rollouts_mode(args, rank, world, local_rank, dist, torch):
     from difffr_b200.cabi import Context
 
     n_cand, n_part, steps = args.candidates, args.rollout_particles, args.rollout_steps
-    scene = scenes.dam_break_scene(n_part, n_boxes=1)
-    cfg = dict(CFG)
-    cfg.update(cfl_method=0, time_step_size=1.0e-3, uniform_acc_rb_time=0.02, target_time=steps * 1.0e-3 - 0.02 - 0.5e-3)
     rng = np.random.default_rng(12)
-    cands = [(rng.normal(size=3), rng.normal(size=3)) for _ in range(n_cand)]
-    body = [i for i, b in enumerate(scene["bodies"]) if b["dynamic"]][0]
+    real = args.rollout_scene == "high_diving"
+    if real:
+        # the scene itself: diff-high-diving-duck.json as the host loader parsed and sampled it (the inputs of the golden
+        # tests/golden/paper_high_diving.npz: 118,389 fluid particles on the lattice, the duck + four static meshes with
+        # 238 k samples, the box emitter), whole trajectories (targetTime 2.3 s); design variable = the duck's initial
+        # angular velocity, as in opt-ng.py --taskType high-diving
+        from difffr_b200.cabi import Config
 
-    def make():
-        return scenes.build_context(lambda **k: Context(device=local_rank, **k), scene, **cfg)
+        g = np.load(os.path.join(ROOT, "tests", "golden", "paper_high_diving.npz"))
+        nb = int(g["n_bodies"])
+        body = [i for i in range(nb) if int(g[f"body{i}_dynamic"])][0]
+        cands = [(np.asarray(g[f"body{body}_init_v"], dtype=np.float64), rng.normal(size=3)) for _ in range(n_cand)]
+        steps = 1 << 20
+
+        def make():
+            ctx = Context(config=Config.from_buffer_copy(g["config_bytes"].tobytes()), device=local_rank)
+            ctx.set_fluid(g["fluid_x"], g["fluid_v"])
+            for i in range(nb):
+                ctx.add_body(g[f"body{i}_samples"].astype(np.float64), bool(g[f"body{i}_dynamic"]), float(g[f"body{i}_density"]),
+                             g[f"body{i}_translation"], g[f"body{i}_rotation"])
+            for k in range(int(g["n_emitters"])):
+                wh, vse = g[f"emitter{k}_wh"], g[f"emitter{k}_vse"]
+                ctx.add_emitter(width=int(wh[0]), height=int(wh[1]), position=g[f"emitter{k}_position"], rotation=g[f"emitter{k}_rotation"],
+                                velocity=float(vse[0]), emit_start=float(vse[1]), emit_end=float(vse[2]))
+            ctx.finalize()
+            return ctx
+    else:
+        scene = scenes.dam_break_scene(n_part, n_boxes=1)
+        cfg = dict(CFG)
+        cfg.update(cfl_method=0, time_step_size=1.0e-3, uniform_acc_rb_time=0.02, target_time=steps * 1.0e-3 - 0.02 - 0.5e-3)
+        cands = [(rng.normal(size=3), rng.normal(size=3)) for _ in range(n_cand)]
+        body = [i for i, b in enumerate(scene["bodies"]) if b["dynamic"]][0]
+
+        def make():
+            return scenes.build_context(lambda **k: Context(device=local_rank, **k), scene, **cfg)
 
     def barrier():
         if dist is not None:
@@ -446,15 +473,18 @@ def rollouts_mode(args, rank, world, local_rank, dist, torch):
     if rank != 0:
         return
     c = results["concurrent"]
-    value = nf * c["steps"] / c["wall"]
+    value = nf * c["steps"] / c["wall"]  # (emitted particles not counted: a lower bound on the real scene)
     line = {
         "metric": "fwd+adjoint particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * c["wall"] / max(c["steps"], 1) * world * conc, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"population of {n_cand} independent rollouts (BASELINE.json configs[3]: CMA-ES-sized population, candidates from "
-                               f"numpy default_rng(12)); synthetic dam break + 1 dynamic box at the high-diving scene's size ({nf} fluid particles), "
-                               f"{steps} steps per trajectory, fixed h = 1e-3; forward step + Jacobians + sensitivity chain rule",
-                   "particles_per_rollout": nf, "rollouts": n_cand, "steps_per_rollout": steps,
+        "config": {"workload": (f"population of {n_cand} independent rollouts (BASELINE.json configs[3]: CMA-ES-sized population, candidates from "
+                                f"numpy default_rng(12)); " +
+                                (f"diff-high-diving-duck.json itself ({nf} fluid particles + emitter, whole trajectories of targetTime 2.3 s, "
+                                 f"{c['steps'] // max(n_cand, 1)} steps on average)" if real else
+                                 f"synthetic dam break + 1 dynamic box at the high-diving scene's size ({nf} fluid particles), "
+                                 f"{steps} steps per trajectory, fixed h = 1e-3") + "; forward step + Jacobians + sensitivity chain rule"),
+                   "particles_per_rollout": nf, "rollouts": n_cand, "steps_per_rollout": c["steps"] // max(n_cand, 1),
                    "parallelism": f"candidates sharded over {world} GPU(s), {conc} contexts side by side per GPU; no data-path collective",
                    "l2": "several independent working sets per GPU, each larger than its share of the 126 MB L2; no flush needed"},
         "rollouts_per_s": n_cand / c["wall"], "seconds_per_population": c["wall"], "concurrency": conc,
@@ -488,6 +518,8 @@ def main():
     ap.add_argument("--rollout-particles", type=int, default=118389, help=argparse.SUPPRESS)
     ap.add_argument("--rollout-steps", type=int, default=200, help=argparse.SUPPRESS)
     ap.add_argument("--no-serial-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--rollout-scene", default="synthetic", choices=["synthetic", "high_diving"],
+                    help="--mode rollouts: the synthetic scene of the high-diving size (default, 200 steps) or diff-high-diving-duck.json itself")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
