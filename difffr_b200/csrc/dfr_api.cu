@@ -172,7 +172,7 @@ struct dfr_context {
     bool p2p = false;
     double4 *peer_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *peer_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long *peer_lo_flags = nullptr, *peer_hi_flags = nullptr;
-    void *ipc_opened[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *ipc_opened[14] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> flags;    // [0] raised by the low neighbour, [1] by the high one
     DevBuf<char> ipc_stage;
     DevBuf<unsigned long long> seq;      // [0] ghost-update passes signalled, [1] mailbox all-reduces done: on the device, never reset
@@ -182,6 +182,11 @@ struct dfr_context {
     SlabMail mail;
     bool mail_ok = false;
     std::vector<void *> ipc_more;
+    // device-side particle exchange of replayed steps (dfr_slab.cuh: SlabXchg): my receive area + the neighbours', mapped
+    DevBuf<char> xin;
+    SlabXchg xchg;
+    bool xchg_ok = false;
+    bool h_stale = false;                // h_ranges / launch_nf are behind the device (replayed steps do not read back)
     long long sync_rows = 0;             // rows one ghost update moves (both directions), from the last exchange
     int64_t cap_syncs_static = 0, cap_syncs_div = 0, cap_syncs_prs = 0;  // ghost updates per replayed step / iteration
     int64_t *cap_sync_counter = nullptr;
@@ -433,13 +438,14 @@ int build_dyn_grid(dfr_context *c) {
 
 int build_neighbor_lists(dfr_context *c);
 int slab_exchange_and_sort(dfr_context *c);
+int slab_exchange_device(dfr_context *c);
 // CompactNSearch replacement: counting sort of the fluid into cell order + neighbour lists
 int build_neighbors(dfr_context *c) {
   const int nc = c->P.grid.ncells;
   const int n = c->launch_nf;
   const int *nf_ptr = &c->dSt.p->nf;
   if (c->slab.on) {
-    int rc = slab_exchange_and_sort(c);
+    int rc = c->capturing ? slab_exchange_device(c) : slab_exchange_and_sort(c);
     if (rc) return rc;
     return build_neighbor_lists(c);
   }
@@ -490,6 +496,7 @@ int sync_state(dfr_context *c) {
   CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (c->hSt->error_flags & 32) return fail(c, DFR_ERR_STATE, "slab: timed out waiting for a neighbour's ghost rows (did a peer fail?)");
+  if (c->hSt->error_flags & 64) return fail(c, DFR_ERR_STATE, "slab: ghost layers do not match the neighbours' boundary layers");
   if (c->hSt->error_flags & 16) return fail(c, DFR_ERR_STATE, "slab: a particle moved further than one ghost layer in one step");
   if (c->hSt->error_flags & 8) return fail(c, DFR_ERR_CAPACITY, "slab: export buffer too small");
   if (c->hSt->error_flags) {
@@ -697,12 +704,12 @@ GhostOut ghost_out(dfr_context *c, int which) {
   std::memset(&g, 0, sizeof(g));
   auto &S = c->slab;
   if (!S.on || !S.p2p) return g;
-  // row ranges and the low neighbour's own_end are read on the device (StepState::slab_ranges; S.counts[3] holds what
-  // the low neighbour sent with the layer counts of the last exchange)
+  // row ranges and the low neighbour's own_end are read on the device (StepState::slab_ranges; the header of my receive
+  // area holds what the low neighbour sent with the layer counts of the last exchange)
   if (S.G.has_lo) g.lo = S.peer_lo[which];
   if (S.G.has_hi) g.hi = S.peer_hi[which];
   g.ranges = c->dSt.p->slab_ranges;
-  g.lo_nb_own_end = S.counts.p + 3;
+  g.lo_nb_own_end = xchg_hdr(S.xin.p) + XH_LO_OWN_END;
   return g;
 }
 
@@ -760,9 +767,9 @@ int slab_p2p_setup(dfr_context *c) {
   const char *env = getenv("DFR_SLAB_TRANSPORT");
   int want = !(env && std::string(env) == "nccl");
   CU(S.flags.alloc(8));
-  const int NH = 6;
+  const int NH = 7;
   CU(S.ipc_stage.alloc(3 * NH * sizeof(cudaIpcMemHandle_t) + 16));
-  void *mine[NH] = {c->xk.p, c->xrho.p, c->normal.p, c->vel[0].p, c->vel[1].p, S.flags.p};
+  void *mine[NH] = {c->xk.p, c->xrho.p, c->normal.p, c->vel[0].p, c->vel[1].p, S.flags.p, S.xin.p};
   std::vector<cudaIpcMemHandle_t> h(3 * NH);
   std::memset(h.data(), 0, h.size() * sizeof(cudaIpcMemHandle_t));
   int ok = want;
@@ -797,8 +804,10 @@ int slab_p2p_setup(dfr_context *c) {
       S.ipc_opened[side * NH + k] = ptr;
       if (k < 5)
         (side == 0 ? S.peer_lo : S.peer_hi)[k] = (double4 *)ptr;
-      else
+      else if (k == 5)
         (side == 0 ? S.peer_lo_flags : S.peer_hi_flags) = (unsigned long long *)ptr;
+      else
+        (side == 0 ? S.xchg.peer_lo : S.xchg.peer_hi) = (char *)ptr;
     }
   }
   // ---- the mailboxes of ALL ranks: residual sums, the CFL maximum and the per-body rows are all-reduced by one small
@@ -864,6 +873,9 @@ int slab_p2p_setup(dfr_context *c) {
   CU(cudaStreamSynchronize(c->stream));
   S.p2p = both[0] != 0;
   S.mail_ok = S.p2p && both[1] != 0;
+  // the particle exchange of replayed steps runs over the same mappings (DFR_SLAB_HOST_EXCHANGE=1: keep the NCCL exchange
+  // with its two read-backs at the head of every step; the variable must be set on all ranks alike)
+  S.xchg_ok = S.mail_ok && getenv_int("DFR_SLAB_HOST_EXCHANGE") == 0;
   return DFR_OK;
 }
 
@@ -873,8 +885,13 @@ int slab_exchange_and_sort(dfr_context *c) {
   auto &S = c->slab;
   NcclApi *N = nccl_api(nullptr);
   const int a = c->cur, b = 1 - c->cur;
+  if (S.h_stale) {  // replayed steps went by: every dfr_step ends with a read-back of the step state
+    std::memcpy(S.h_ranges, c->hSt->slab_ranges, sizeof(S.h_ranges));
+    S.h_stale = false;
+  }
   const int own_begin = S.h_ranges[0], own_end = S.h_ranges[1];
   const int n_own = own_end - own_begin;
+  int *const hdr = xchg_hdr(S.xin.p);
   CU(cudaMemsetAsync(S.counts.p, 0, 8 * sizeof(int), c->stream));
   LAUNCH(c, k_slab_select, cdiv(n_own, 128), 128, c->P, S.G, c->dSt.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p,
          c->pid[a].p, c->pstate[a].p, S.send_cap, S.s_pos[0].p, S.s_vel[0].p, S.s_misc[0].p, S.s_pos[1].p, S.s_vel[1].p, S.s_misc[1].p,
@@ -933,8 +950,8 @@ int slab_exchange_and_sort(dfr_context *c) {
   if (rc) return rc;
   LAUNCH(c, k_bin_scatter, cdiv(n_src, 128), 128, (const int *)nullptr, n_src, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
          c->sorted_src_f.p);
-  LAUNCH(c, k_bin_sort_cells_by_id, cdiv(n_src, 128), 128, n_src, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p,
-         c->sorted_src_f.p, c->pid[a].p + own_begin);
+  LAUNCH(c, k_bin_sort_cells_by_id, cdiv(n_src, 128), 128, (const int *)nullptr, n_src, (const int *)nullptr, c->cell_start_f.p, c->cell_of_p.p,
+         c->rank_in_cell.p, c->sorted_src_f.p, c->pid[a].p + own_begin);
   LAUNCH(c, k_permute_fluid, cdiv(n_src, 128), 128, c->dSt.p, c->sorted_src_f.p, pos + own_begin, vel + own_begin, c->kappa[a].p + own_begin,
          c->kappav[a].p + own_begin, c->pid[a].p + own_begin, c->pstate[a].p + own_begin, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p,
          c->kappav[b].p, c->pid[b].p, c->pstate[b].p);
@@ -946,14 +963,14 @@ int slab_exchange_and_sort(dfr_context *c) {
   NC(N->GroupStart());
   if (S.G.has_lo) {
     NC(N->Send(&c->dSt.p->slab_ranges[5], 1, ncclInt, S.rank - 1, S.comm, c->stream));
-    NC(N->Recv(S.counts.p + 2, 2, ncclInt, S.rank - 1, S.comm, c->stream));  // its bl_hi count, its own_end
+    NC(N->Recv(hdr + XH_LO_BL, 2, ncclInt, S.rank - 1, S.comm, c->stream));  // its bl_hi count, its own_end
   }
   if (S.G.has_hi) {
     NC(N->Send(&c->dSt.p->slab_ranges[6], 2, ncclInt, S.rank + 1, S.comm, c->stream));  // my bl_hi count, my own_end (ranges[7])
-    NC(N->Recv(S.counts.p + 4, 1, ncclInt, S.rank + 1, S.comm, c->stream));
+    NC(N->Recv(hdr + XH_HI_BL, 1, ncclInt, S.rank + 1, S.comm, c->stream));
   }
   NC(N->GroupEnd());
-  CU(cudaMemcpyAsync(S.h_counts, S.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(S.h_counts, hdr, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   rc = sync_state(c);
   if (rc) return rc;
   std::memcpy(S.h_ranges, c->hSt->slab_ranges, sizeof(S.h_ranges));
@@ -966,6 +983,46 @@ int slab_exchange_and_sort(dfr_context *c) {
   }
   S.sync_rows = (S.G.has_lo ? (S.h_ranges[2] - S.h_ranges[0]) + S.h_ranges[0] : 0) +
                 (S.G.has_hi ? (S.h_ranges[1] - S.h_ranges[3]) + (S.h_ranges[4] - S.h_ranges[1]) : 0);
+  return DFR_OK;
+}
+
+// The same on the device (replayed steps, dfr_slab.cuh "Device-side particle exchange"): peer stores + two flag passes;
+// ranges, counts and capacities are read and checked by the kernels, grids are sized for the capacities.
+int slab_exchange_device(dfr_context *c) {
+  auto &S = c->slab;
+  const int a = c->cur, b = 1 - c->cur;
+  const int gcap = cdiv(c->nf_cap, 128);
+  const int nc = c->P.grid.ncells;
+  const SlabXchg &X = S.xchg;
+  StepState *st = c->dSt.p;
+  unsigned long long *flo = S.G.has_lo ? S.peer_lo_flags + 1 : (unsigned long long *)nullptr;
+  unsigned long long *fhi = S.G.has_hi ? S.peer_hi_flags + 0 : (unsigned long long *)nullptr;
+  // I am the high neighbour of my low neighbour: my rows go into the "from high" half of its area, and vice versa
+  double4 *nul = nullptr;
+  CU(cudaMemsetAsync(S.counts.p, 0, 8 * sizeof(int), c->ls));
+  LAUNCH(c, k_slab_select, gcap, 128, c->P, S.G, st, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p, c->pid[a].p,
+         c->pstate[a].p, S.send_cap, X.peer_lo ? xchg_rows(X.peer_lo, 1, 0, X.cap) : nul, X.peer_lo ? xchg_rows(X.peer_lo, 1, 1, X.cap) : nul,
+         X.peer_lo ? xchg_rows(X.peer_lo, 1, 2, X.cap) : nul, X.peer_hi ? xchg_rows(X.peer_hi, 0, 0, X.cap) : nul,
+         X.peer_hi ? xchg_rows(X.peer_hi, 0, 1, X.cap) : nul, X.peer_hi ? xchg_rows(X.peer_hi, 0, 2, X.cap) : nul, S.counts.p, &st->error_flags);
+  LAUNCH(c, k_slab_xchg_post_rows, 1, 32, S.counts.p, X, flo, fhi, (volatile unsigned long long *)S.flags.p, S.seq.p + 0, 5000000000ull,
+         &st->error_flags);
+  LAUNCH(c, k_slab_xchg_unpack, std::max(1, cdiv(2 * (int64_t)S.send_cap, 128)), 128, st, X, (int)c->nf_cap, c->pos[a].p, c->vel[c->vcur].p,
+         c->kappa[a].p, c->kappav[a].p, c->pid[a].p, c->pstate[a].p);
+  // sort [own_begin, own_end + received) by (cell, id) into the other buffers
+  CU(cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->ls));
+  LAUNCH(c, k_slab_bin_count, gcap, 128, c->P, st, c->pos[a].p, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
+  int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
+  if (rc) return rc;
+  LAUNCH(c, k_bin_scatter, gcap, 128, (const int *)&st->nf, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p, c->sorted_src_f.p);
+  LAUNCH(c, k_bin_sort_cells_by_id, gcap, 128, (const int *)&st->nf, 0, (const int *)&st->own_begin, c->cell_start_f.p, c->cell_of_p.p,
+         c->rank_in_cell.p, c->sorted_src_f.p, c->pid[a].p);
+  LAUNCH(c, k_permute_fluid, gcap, 128, st, c->sorted_src_f.p, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p, c->pid[a].p,
+         c->pstate[a].p, c->pos[b].p, c->vel[1 - c->vcur].p, c->kappa[b].p, c->kappav[b].p, c->pid[b].p, c->pstate[b].p,
+         (const int *)&st->own_begin);
+  c->cur = b;
+  c->vcur = 1 - c->vcur;
+  LAUNCH(c, k_slab_ranges, 1, 32, c->P, S.G, st, c->cell_start_f.p);
+  LAUNCH(c, k_slab_xchg_post_layers, 1, 32, st, X, flo, fhi, (volatile unsigned long long *)S.flags.p, S.seq.p + 0, 5000000000ull);
   return DFR_OK;
 }
 
@@ -1290,9 +1347,9 @@ int launch_step(dfr_context *c) {
     rc = contact_sort_tick(c);
     if (rc) return rc;
   }
-  if (c->capturing && c->slab.on)
-    // a slab-decomposed step is replayed from the list build on: k_begin_step and the particle exchange (NCCL transfers
-    // whose sizes the host reads back) stay on the stream, see enqueue_steps
+  if (c->capturing && c->slab.on && !c->slab.xchg_ok)
+    // DFR_SLAB_HOST_EXCHANGE=1: the step is replayed from the list build on; k_begin_step and the particle exchange (NCCL
+    // transfers whose sizes the host reads back) stay on the stream, see enqueue_steps
     rc = build_neighbor_lists(c);
   else {
     LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, (c->capturing && fuse_nonpressure_enabled(c)) ? 1 : 0);
@@ -1480,6 +1537,7 @@ int reset_device_state(dfr_context *c) {
     c->slab.h_ranges[0] = 0;
     c->slab.h_ranges[1] = c->slab.h_ranges[2] = c->slab.h_ranges[3] = c->slab.h_ranges[4] = st.nf;
     c->slab.exchanged_bytes = 0;
+    c->slab.h_stale = false;
     c->launch_nf = st.nf;
   }
   CU(cudaMemcpyAsync(c->dSt.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
@@ -1632,7 +1690,7 @@ void dfr_destroy(dfr_context *c) {
   for (void *p : c->slab.ipc_more)
     if (p) cudaIpcCloseMemHandle(p);
   c->slab.seq.free(); c->slab.mbox.free(); c->slab.mflag.free();
-  c->slab.r_misc.free(); c->slab.counts.free(); c->slab.body_buf.free(); c->slab.flags.free(); c->slab.ipc_stage.free();
+  c->slab.r_misc.free(); c->slab.counts.free(); c->slab.xin.free(); c->slab.body_buf.free(); c->slab.flags.free(); c->slab.ipc_stage.free();
   if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
   if (c->slab.h_stage) cudaFreeHost(c->slab.h_stage);
   if (c->slab.comm && nccl_api(nullptr)) nccl_api(nullptr)->CommDestroy(c->slab.comm);
@@ -1970,6 +2028,11 @@ int dfr_finalize(dfr_context *c) {
     }
     CU(S.r_misc.alloc(2 * (size_t)S.send_cap));
     CU(S.counts.alloc(8));
+    CU(S.xin.alloc(xchg_bytes(S.send_cap)));
+    std::memset(&S.xchg, 0, sizeof(S.xchg));
+    S.xchg.mine = S.xin.p;
+    S.xchg.cap = S.send_cap;
+    S.xchg_ok = false;
     CU(S.body_buf.alloc(std::max<size_t>(c->bodies.size(), 1) * ACC_N));
     if (cudaMallocHost((void **)&S.h_counts, 8 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");
   }
@@ -2266,6 +2329,27 @@ int enqueue_steps(dfr_context *c, int n_steps, int gated, StepBatch &B) {
         if (rc) return rc;
         continue;
       }
+      {  // row capacities: local buffers, re-allocating and re-recording changes nothing the neighbours can see
+        int rc = relax_list_capacity(c);
+        if (rc) return rc;
+      }
+      if (c->slab.xchg_ok) {  // the whole step is one replay: particle exchange over peer memory, nothing read back
+        dfr_context::StepGraph &sgx = c->step_graph[0][c->cur];
+        if (!sgx.exec) {
+          int rc = capture_step_graph(c, 0);
+          if (rc) return rc;
+        }
+        if (B.graph_steps == 0) {
+          B.it0 = c->hSt->total_iters;
+          B.itv0 = c->hSt->total_iters_v;
+        }
+        CU(cudaGraphLaunch(sgx.exec, c->stream));
+        c->cur = 1 - c->cur;
+        c->slab.h_stale = true;
+        B.graph_steps++;
+        B.last = &sgx;
+        continue;
+      }
       LAUNCH(c, k_begin_step, 1, 32, c->P, c->dSt.p, c->dBodies.p, fuse_nonpressure_enabled(c) ? 1 : 0);
       int rc = slab_exchange_and_sort(c);  // leaves hSt current
       if (rc) return rc;
@@ -2327,6 +2411,11 @@ void account_graph_launches(dfr_context *c, const StepBatch &B, int64_t steps_ex
   if (!B.last) return;
   c->launches += steps_executed * B.last->n_static + (c->hSt->total_iters_v - B.itv0) * B.last->n_div_body +
                  (c->hSt->total_iters - B.it0) * B.last->n_prs_body;
+  if (c->slab.on && c->slab.h_stale) {  // device-side exchange: the ranges of the last replayed step, read back with the step state
+    const int *r = c->hSt->slab_ranges;
+    c->slab.sync_rows = (c->slab.G.has_lo ? (r[2] - r[0]) + r[0] : 0) + (c->slab.G.has_hi ? (r[1] - r[3]) + (r[4] - r[1]) : 0);
+    c->slab.exchanged_bytes += c->slab.sync_rows * 96 * steps_executed;  // exported boundary layers + imported ghosts, 96 B each
+  }
   if (c->slab.on)  // ghost updates of the replayed steps (32-byte rows; the row count of the last exchange stands for all of them)
     c->slab.exchanged_bytes += c->slab.sync_rows * 32 * (steps_executed * c->slab.cap_syncs_static +
                                                          (c->hSt->total_iters_v - B.itv0) * c->slab.cap_syncs_div +

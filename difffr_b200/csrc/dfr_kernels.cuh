@@ -540,10 +540,10 @@ __global__ void k_bin_sort_cells_by_particle(const int *n_ptr, int n_fixed, cons
 __global__ void k_permute_fluid(const StepState *st, const int *sorted_src, const double4 *pos_in, const double4 *vel_in,
                                 const double *kappa_in, const double *kappav_in, const int *id_in, const int *state_in,
                                 double4 *pos_out, double4 *vel_out, double *kappa_out, double *kappav_out, int *id_out,
-                                int *state_out) {
+                                int *state_out, const int *src_base = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->nf) return;
-  const int s = sorted_src[i];
+  const int s = sorted_src[i] + (src_base ? *src_base : 0);  // slab mode: the source range starts at own_begin
   pos_out[i] = pos_in[s];
   vel_out[i] = vel_in[s];
   kappa_out[i] = kappa_in[s];

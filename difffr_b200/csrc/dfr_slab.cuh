@@ -82,10 +82,12 @@ __global__ void k_slab_set_nf(StepState *st, int nf) {
 // cells are sorted by source slot (k_bin_sort_cells); here by particle id, so that two ranks holding the same particles
 // in a cell order them identically
 // (driven from the particles like k_bin_sort_cells_by_particle: the particle that drew rank 0 sorts its cell)
-__global__ void k_bin_sort_cells_by_id(int n, const unsigned int *cell_start, const int *cell_of_particle, const int *rank_in_cell,
-                                       int *sorted_src, const int *pid_src) {
+__global__ void k_bin_sort_cells_by_id(const int *n_ptr, int n_fixed, const int *base_ptr, const unsigned int *cell_start,
+                                       const int *cell_of_particle, const int *rank_in_cell, int *sorted_src, const int *pid_src) {
+  const int n = n_ptr ? *n_ptr : n_fixed;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n || rank_in_cell[t] != 0) return;
+  if (base_ptr) pid_src += *base_ptr;
   const int c = cell_of_particle[t];
   const int s = (int)cell_start[c], e = (int)cell_start[c + 1];
   int *a = sorted_src + s;
@@ -233,13 +235,13 @@ __global__ void __launch_bounds__(256) k_slab_sum_f64(StepState *st, const SlabM
 // One thread: release my writes at system scope, raise the counter in both neighbours' flag words, then spin on mine.
 // flags[0] is written by the low neighbour, flags[1] by the high one.  A wait that lasts longer than `timeout_ns` gives
 // up and raises error bit 32 (a peer that failed must not hang this GPU).
-__global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, volatile unsigned long long *my_flags,
-                                   unsigned long long *pass_counter, unsigned long long timeout_ns, int *error_flags) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ bool slab_signal_wait(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag,
+                                                 volatile unsigned long long *my_flags, unsigned long long *pass_counter,
+                                                 unsigned long long timeout_ns, int *error_flags) {
   // the pass number lives on the device (both neighbours make the same sequence of calls; never reset, like the flags),
   // so that the kernel can be part of a recorded step graph
   const unsigned long long value = ++(*pass_counter);
-  if (*error_flags & 32) return;  // a neighbour already failed to answer once: do not stack further time-outs
+  if (*error_flags & 32) return false;  // a neighbour already failed to answer once: do not stack further time-outs
   __threadfence_system();
   if (peer_lo_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_lo_flag), "l"(value) : "memory");
   if (peer_hi_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_hi_flag), "l"(value) : "memory");
@@ -255,9 +257,109 @@ __global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned lo
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > timeout_ns) {
         atomicOr(error_flags, 32);
-        return;
+        return false;
       }
     }
+  }
+  return true;
+}
+__global__ void k_slab_signal_wait(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, volatile unsigned long long *my_flags,
+                                   unsigned long long *pass_counter, unsigned long long timeout_ns, int *error_flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  slab_signal_wait(peer_lo_flag, peer_hi_flag, my_flags, pass_counter, timeout_ns, error_flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side particle exchange (the head of a replayed slab step: no NCCL call, no host read-back).
+// Every rank exports one receive area (cudaIpc): a header of ints and, per side, room for `cap` (pos, vel, misc)
+// records.  k_slab_select stores the particles of my export layers straight into the neighbours' areas over NVLink,
+// k_slab_xchg_post_rows tells them how many and waits for theirs (same flag protocol as the ghost updates),
+// k_slab_xchg_unpack appends what arrived behind my owned range; after the re-sort k_slab_xchg_post_layers exchanges
+// the sizes of the shared layers (the neighbours' ghost stores need my own_end; a mismatch is an error, not a hang).
+// A neighbour can only write its next step's rows after all of this step's ghost-update passes, which I answer after
+// my unpack: one area per side is enough.
+// ---------------------------------------------------------------------------------------------
+enum { XH_ROWS_LO = 0, XH_ROWS_HI = 1, XH_LO_BL = 2, XH_LO_OWN_END = 3, XH_HI_BL = 4, XH_INTS = 64 };
+struct SlabXchg {
+  char *mine, *peer_lo, *peer_hi;  // receive areas (peer_*: null without that neighbour)
+  int cap;
+};
+__host__ __device__ __forceinline__ int *xchg_hdr(char *area) { return reinterpret_cast<int *>(area); }
+// rows sent by the neighbour on `side` (0: low, 1: high) of the area's owner; arr 0 pos, 1 vel, 2 misc
+__host__ __device__ __forceinline__ double4 *xchg_rows(char *area, int side, int arr, int cap) {
+  return reinterpret_cast<double4 *>(area + XH_INTS * sizeof(int)) + (size_t)(side * 3 + arr) * (size_t)cap;
+}
+__host__ __device__ __forceinline__ size_t xchg_bytes(int cap) { return XH_INTS * sizeof(int) + (size_t)6 * (size_t)cap * sizeof(double4); }
+
+__device__ __forceinline__ double4 ldcv4(const double4 *p) {  // the neighbour wrote these rows: volatile loads
+  const double2 a = __ldcv(reinterpret_cast<const double2 *>(p)), b = __ldcv(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__global__ void k_slab_xchg_post_rows(const int *counts, const SlabXchg X, unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag,
+                                      volatile unsigned long long *my_flags, unsigned long long *pass_counter, unsigned long long timeout_ns,
+                                      int *error_flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (X.peer_lo) xchg_hdr(X.peer_lo)[XH_ROWS_HI] = min(counts[0], X.cap);  // I am its high neighbour
+  if (X.peer_hi) xchg_hdr(X.peer_hi)[XH_ROWS_LO] = min(counts[1], X.cap);
+  slab_signal_wait(peer_lo_flag, peer_hi_flag, my_flags, pass_counter, timeout_ns, error_flags);
+}
+__global__ void k_slab_xchg_unpack(StepState *st, const SlabXchg X, int nf_cap, double4 *pos, double4 *vel, double *kappa, double *kappav,
+                                   int *pid, int *pstate) {
+  const int *h = xchg_hdr(X.mine);
+  const int at = st->own_end;
+  int n_lo = X.peer_lo ? min(max(__ldcv(h + XH_ROWS_LO), 0), X.cap) : 0;
+  int n_hi = X.peer_hi ? min(max(__ldcv(h + XH_ROWS_HI), 0), X.cap) : 0;
+  if (st->error_flags & 32) n_lo = n_hi = 0;  // a neighbour did not answer: the header is stale
+  const int room = max(nf_cap - at, 0);
+  const bool over = n_lo + n_hi > room;
+  if (over) {
+    n_lo = min(n_lo, room);
+    n_hi = min(n_hi, room - n_lo);
+  }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) {
+    st->nf = (at - st->own_begin) + n_lo + n_hi;  // what the re-sort works on: [own_begin, own_end + received)
+    if (over) atomicOr(&st->error_flags, 8);
+  }
+  if (k >= n_lo + n_hi) return;
+  const int side = k < n_lo ? 0 : 1, r = k < n_lo ? k : k - n_lo;
+  const double4 m = ldcv4(xchg_rows(X.mine, side, 2, X.cap) + r);
+  pos[at + k] = ldcv4(xchg_rows(X.mine, side, 0, X.cap) + r);
+  vel[at + k] = ldcv4(xchg_rows(X.mine, side, 1, X.cap) + r);
+  kappa[at + k] = m.x;
+  kappav[at + k] = m.y;
+  pid[at + k] = (int)__double_as_longlong(m.z);
+  pstate[at + k] = (int)__double_as_longlong(m.w);
+}
+// k_bin_count over [own_begin, own_begin + nf) with the range read on the device
+__global__ void k_slab_bin_count(const __grid_constant__ Params P, const StepState *st, const double4 *pos, unsigned int *cell_count,
+                                 int *cell_of_particle, int *rank_in_cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->nf) return;
+  const double4 p = pos[st->own_begin + i];
+  int cx, cy, cz;
+  cell_of(P.grid, p.x, p.y, p.z, cx, cy, cz);
+  const int c = cell_lin(P.grid, cx, cy, cz);
+  cell_of_particle[i] = c;
+  rank_in_cell[i] = (int)atomicAdd(&cell_count[c], 1u);
+}
+__global__ void k_slab_xchg_post_layers(StepState *st, const SlabXchg X, unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag,
+                                        volatile unsigned long long *my_flags, unsigned long long *pass_counter,
+                                        unsigned long long timeout_ns) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (X.peer_lo) xchg_hdr(X.peer_lo)[XH_HI_BL] = st->slab_ranges[5];
+  if (X.peer_hi) {
+    xchg_hdr(X.peer_hi)[XH_LO_BL] = st->slab_ranges[6];
+    xchg_hdr(X.peer_hi)[XH_LO_OWN_END] = st->slab_ranges[7];
+  }
+  const bool ok = slab_signal_wait(peer_lo_flag, peer_hi_flag, my_flags, pass_counter, timeout_ns, &st->error_flags);
+  const int *h = xchg_hdr(X.mine);
+  const int ghost_lo = st->slab_ranges[0], ghost_hi = st->slab_ranges[4] - st->slab_ranges[1];
+  if (!ok || (X.peer_lo && __ldcv(h + XH_LO_BL) != ghost_lo) || (X.peer_hi && __ldcv(h + XH_HI_BL) != ghost_hi)) {
+    // the two sides of a plane disagree about the shared layers: no ghost row may be stored (the ranges would not match)
+    if (ok) atomicOr(&st->error_flags, 64);
+    st->slab_ranges[2] = st->slab_ranges[0];
+    st->slab_ranges[3] = st->slab_ranges[1];
   }
 }
 

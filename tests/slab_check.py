@@ -25,6 +25,8 @@ def main():
     n_particles = int(sys.argv[1]) if len(sys.argv) > 1 else 30000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     manager = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    burst = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # then `bursts` calls of dfr_step(burst)
+    bursts = int(sys.argv[5]) if len(sys.argv) > 5 else (2 if burst else 0)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")  # control plane only (id broadcast, merging the parity dumps)
@@ -49,6 +51,47 @@ def main():
     n = slab.num_fluid
     assert n == len(sc["fluid"])
     worst = 0.0
+    def advance_and_compare(s, k):
+        """k steps in one dfr_step call on both sides (k > 1: replayed steps back to back, nothing read back in between)"""
+        nonlocal worst
+        slab.step(k)
+        info = slab.step_info()
+        owned = torch.tensor([info.num_fluid_particles], dtype=torch.int64)
+        dist.all_reduce(owned)
+        assert int(owned) == n, (int(owned), n)  # every particle is owned by exactly one slab
+        merged = {}
+        for f in FIELDS:
+            a = torch.from_numpy(slab.fluid(f))  # zero except for the ids this rank owns
+            dist.all_reduce(a)
+            merged[f] = a.numpy()
+        if rank == 0:
+            single.step(k)
+            i1 = single.step_info()
+            assert (info.iterations, info.iterations_v) == (i1.iterations, i1.iterations_v), (s, info.iterations, i1.iterations, info.iterations_v, i1.iterations_v)
+            assert abs(info.time_step_size - i1.time_step_size) <= 1e-12 * i1.time_step_size
+            for f in FIELDS:
+                e = rel(merged[f], single.fluid(f))
+                worst = max(worst, e)
+                assert e < 1e-9, (s, f, e)
+            for b in (1, 2):
+                sa, sb = slab.body_state(b), single.body_state(b)
+                for kk in sa:
+                    e = rel(sa[kk], sb[kk])
+                    worst = max(worst, e)
+                    assert e < 1e-9, (s, b, kk, e)
+                for w in range(16):
+                    e = rel(slab.body_grad(b, w), single.body_grad(b, w))
+                    assert e < 1e-7, (s, b, w, e)
+                    if manager:
+                        e = rel(slab.manager_grad(b, b, w), single.manager_grad(b, b, w))
+                        assert e < 1e-7, (s, b, w, e)
+        # rigid bodies are replicated: identical bits on every rank
+        st = torch.from_numpy(np.concatenate([slab.body_state(1)[kk] for kk in ("x", "q", "v", "omega")]))
+        lo, hi = st.clone(), st.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi)
+
     for s in range(steps):
         if s == steps // 2:  # reset in the middle: initial distribution is restored
             slab.reset()
@@ -67,45 +110,11 @@ def main():
                 slab.load_fluid_state_local(st_x[ids], st_v[ids], st_k[ids], st_kv[ids])
             if single:
                 single.load_fluid_state(st_x, st_v, st_k, st_kv)
-        slab.step(1)
-        info = slab.step_info()
-        owned = torch.tensor([info.num_fluid_particles], dtype=torch.int64)
-        dist.all_reduce(owned)
-        assert int(owned) == n, (int(owned), n)  # every particle is owned by exactly one slab
-        merged = {}
-        for f in FIELDS:
-            a = torch.from_numpy(slab.fluid(f))  # zero except for the ids this rank owns
-            dist.all_reduce(a)
-            merged[f] = a.numpy()
-        if rank == 0:
-            single.step(1)
-            i1 = single.step_info()
-            assert (info.iterations, info.iterations_v) == (i1.iterations, i1.iterations_v), (s, info.iterations, i1.iterations, info.iterations_v, i1.iterations_v)
-            assert abs(info.time_step_size - i1.time_step_size) <= 1e-12 * i1.time_step_size
-            for f in FIELDS:
-                e = rel(merged[f], single.fluid(f))
-                worst = max(worst, e)
-                assert e < 1e-9, (s, f, e)
-            for b in (1, 2):
-                sa, sb = slab.body_state(b), single.body_state(b)
-                for k in sa:
-                    e = rel(sa[k], sb[k])
-                    worst = max(worst, e)
-                    assert e < 1e-9, (s, b, k, e)
-                for w in range(16):
-                    e = rel(slab.body_grad(b, w), single.body_grad(b, w))
-                    assert e < 1e-7, (s, b, w, e)
-                    if manager:
-                        e = rel(slab.manager_grad(b, b, w), single.manager_grad(b, b, w))
-                        assert e < 1e-7, (s, b, w, e)
-        # rigid bodies are replicated: identical bits on every rank
-        st = torch.from_numpy(np.concatenate([slab.body_state(1)[k] for k in ("x", "q", "v", "omega")]))
-        lo, hi = st.clone(), st.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert torch.equal(lo, hi)
+        advance_and_compare(s, 1)
+    for r in range(bursts):  # several steps per call
+        advance_and_compare(steps + r, burst)
     si = slab.slab_info()
-    print(f"rank {rank}: owned {si['owned']} ghosts {si['ghosts']} exchanged {si['exchanged_bytes'] / 1e6:.1f} MB ({si['transport']}) over {steps - steps // 2} steps; worst rel diff {worst:.2e}", flush=True)
+    print(f"rank {rank}: owned {si['owned']} ghosts {si['ghosts']} exchanged {si['exchanged_bytes'] / 1e6:.1f} MB ({si['transport']}) over {steps - steps // 2 + burst * bursts} steps; worst rel diff {worst:.2e}", flush=True)
     dist.barrier()
     if rank == 0:
         print("SLAB_CHECK_OK", flush=True)

@@ -16,19 +16,34 @@ def _gpus():
     return torch.cuda.device_count()
 
 
+def _run(n_particles, steps, manager, port, env_extra=None, burst=0, ranks=2):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_check.py"), str(n_particles), str(steps), str(manager), str(burst)]
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "SLAB_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
 @pytest.mark.parametrize("manager,transport", [(0, "p2p"), (1, "p2p"), (0, "nccl")])
 def test_two_slabs_equal_one_domain(manager, transport):
     """transport: ghost rows written by the producing kernels into the neighbour's memory (peer stores, default) or
     shipped by NCCL send/recv after every producing kernel (DFR_SLAB_TRANSPORT=nccl) - the fused k_rho passes carry a
-    second ghost array in both cases."""
+    second ghost array in both cases.  Six or seven steps with a reset and a state load in between: all of them on the
+    stream path (the four steps after finalize / reset / load are)."""
     if _gpus() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29517 + manager + (4 if transport == "nccl" else 0)), os.path.join(ROOT, "tests", "slab_check.py"), "30000",
-           str(6 + manager),  # an odd step count makes slab_check load a state through the per-rank form
-           str(manager)]
-    env = dict(os.environ)
-    if transport == "nccl":
-        env["DFR_SLAB_TRANSPORT"] = "nccl"
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert res.returncode == 0 and "SLAB_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    # an odd step count makes slab_check load a state through the per-rank form
+    _run(30000, 6 + manager, manager, 29517 + manager + (4 if transport == "nccl" else 0),
+         {"DFR_SLAB_TRANSPORT": "nccl"} if transport == "nccl" else None)
+
+
+@pytest.mark.parametrize("exchange", ["device", "host"])
+def test_replayed_slab_steps_equal_one_domain(exchange):
+    """16 single steps (reset after 8, state load after 9: steps 5-8 and 14-16 are graph replays) and then two calls of
+    dfr_step(5), i.e. replays back to back with nothing read back in between.  exchange: the particle exchange at the head
+    of a replayed step over peer memory inside the graph (default) or by NCCL with two host read-backs
+    (DFR_SLAB_HOST_EXCHANGE=1)."""
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _run(30000, 16, 1, 29531 + (1 if exchange == "host" else 0), {"DFR_SLAB_HOST_EXCHANGE": "1"} if exchange == "host" else None, burst=5)
