@@ -608,16 +608,51 @@ struct GridView {
 };
 
 // Visits every point of `g` within the support radius of (px,py,pz); f(index) with index = base + point.
+// -DDFR_NBR_TRIM=1 trims the (2 reach + 1)^3 stencil to the cells the support sphere can reach: a row whose cell slab
+// lies further away than the radius in (y, z) is skipped, the others are cut in x to the cells whose near face is still
+// inside (squared face distances, 1e-9 relative slack - far more than the rounding of cell_of; points outside the grid
+// sit in edge cells, whose far side is open, so the near-face test holds for them too).  84 of 125 cells and 21.6 of
+// 25 rows are left for reach 2, order and set of the accepted points are unchanged (the parity tests pass) - and
+// k_nbr_build gets SLOWER, 386 -> 434 us at 1 M particles: a warp still runs the longest row of its 32 lanes, so the
+// trip counts barely fall while every row pays the face arithmetic.  Off by default (profiles/r2_gather_analysis.md).
+#ifndef DFR_NBR_TRIM
+#define DFR_NBR_TRIM 0
+#endif
 template <class F>
 __device__ __forceinline__ void for_each_in_range(const Params &P, const GridView &g, double px, double py, double pz, int self, F f) {
   int cx, cy, cz;
   cell_of(P.grid, px, py, pz, cx, cy, cz);
   const int R = P.grid.reach;
   const int xlo = max(cx - R, 0), xhi = min(cx + R, P.grid.nx - 1);
-  for (int z = max(cz - R, 0); z <= min(cz + R, P.grid.nz - 1); z++)
+#if DFR_NBR_TRIM
+  const double cell = 1.0 / P.grid.inv_cell;
+  const double r2m = P.r2 * (1.0 + 1e-9);
+  const double ry = py - P.grid.oy, rz = pz - P.grid.oz, rx = px - P.grid.ox;
+#endif
+  for (int z = max(cz - R, 0); z <= min(cz + R, P.grid.nz - 1); z++) {
+#if DFR_NBR_TRIM
+    // distance to the slab of cell layer z (0 for my own layer and when I sit beyond the face)
+    const double dz = z < cz ? rz - (double)(z + P.grid.z_shift + 1) * cell : (z > cz ? (double)(z + P.grid.z_shift) * cell - rz : 0.0);
+    const double dz2 = dz > 0.0 ? dz * dz : 0.0;
+    if (dz2 >= r2m) continue;
+#endif
     for (int y = max(cy - R, 0); y <= min(cy + R, P.grid.ny - 1); y++) {
-      const int s = (int)g.cell_start[cell_lin(P.grid, xlo, y, z)];
-      const int e = (int)g.cell_start[cell_lin(P.grid, xhi, y, z) + 1];
+      int xl = xlo, xh = xhi;
+#if DFR_NBR_TRIM
+      const double dy = y < cy ? ry - (double)(y + 1) * cell : (y > cy ? (double)y * cell - ry : 0.0);
+      const double d2 = dz2 + (dy > 0.0 ? dy * dy : 0.0);
+      if (d2 >= r2m) continue;
+      for (xl = cx; xl > xlo; xl--) {  // take cell xl - 1 while its high face is in reach
+        const double d = rx - (double)xl * cell;
+        if (d > 0.0 && d * d + d2 >= r2m) break;
+      }
+      for (xh = cx; xh < xhi; xh++) {
+        const double d = (double)(xh + 1) * cell - rx;
+        if (d > 0.0 && d * d + d2 >= r2m) break;
+      }
+#endif
+      const int s = (int)g.cell_start[cell_lin(P.grid, xl, y, z)];
+      const int e = (int)g.cell_start[cell_lin(P.grid, xh, y, z) + 1];
       for (int p = s; p < e; p++) {
         const int j = g.sorted_src ? g.sorted_src[p] : p;
         if (j == self) continue;
@@ -625,6 +660,7 @@ __device__ __forceinline__ void for_each_in_range(const Params &P, const GridVie
         if (dist2_exact(px, py, pz, q.x, q.y, q.z) < P.r2) f(g.base + j);
       }
     }
+  }
 }
 
 // Single scan: fluid->fluid and fluid->boundary neighbour lists in a warp-interleaved ELL layout
