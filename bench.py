@@ -95,8 +95,25 @@ class ClockSampler:
         import datetime
 
         self.window = datetime.datetime.now()
+        self.window_pc = time.perf_counter()
 
     def start(self):
+        # NVML in a thread (one sample every ~2 ms: a 20-step timed region is only ~60 ms long); nvidia-smi -lms as fallback
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml_samples = []
+            self.nvml_stop = False
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 - no NVML binding / no permission: use the command-line tool
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -105,11 +122,48 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.nvml_stop:
+            try:
+                t = time.perf_counter()
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.handle))
+                try:
+                    power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:  # noqa: BLE001
+                    power = None
+                self.nvml_samples.append((t, sm, mask, power))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def _stop_nvml(self):
+        t_end = time.perf_counter()
+        self.nvml_stop = True
+        self.thread.join(timeout=1.0)
+        t0 = getattr(self, "window_pc", None)
+        inside = [x for x in self.nvml_samples if (t0 is None or x[0] >= t0) and x[0] <= t_end]
+        note = None
+        if not inside:
+            inside, note = self.nvml_samples, "no sample fell inside the timed region; all samples of the run (warm-up included) are used"
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        reasons = sorted({nm for x in inside for bit, nm in names.items() if x[2] & bit})
+        power = [x[3] for x in inside if x[3] is not None]
+        out = {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.sm_max,
+               "power_w_max": max(power) if power else None, "samples": len(inside), "reasons": reasons, "source": "nvml"}
+        if note:
+            out["note"] = note
+        return out
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nvml", None) is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         import datetime

@@ -1281,16 +1281,18 @@ int contact_rest_state(dfr_context *c) {
 // needs a host read-back right after the list build, so it is only made while rows may plausibly overflow: in the
 // first steps after finalize / reset / load, and whenever the longest row of the previous step was above half the
 // capacity (a row does not double within one step of a CFL-limited simulation).  Otherwise an overflow still surfaces
-// as DFR_ERR_CAPACITY at the step's first read-back.  Slab-decomposed contexts keep the fixed capacities.
+// as DFR_ERR_CAPACITY at the step's first read-back.  Slab-decomposed contexts only come here in the steps after
+// finalize / reset / load (enqueue_steps counts them down) and under profiling: always checked; the lists are local, so
+// a rank that rebuilds its lists changes nothing its neighbours can see.
 int ensure_list_capacity(dfr_context *c) {
-  if (c->slab.on) return DFR_OK;
-  const bool risky = c->fresh_steps > 0 || 2 * (int)c->hSt->list_used_f > c->cap_f || 2 * (int)c->hSt->list_used_b > c->cap_b ||
-                     2ull * c->hSt->list_used_d > c->cap_d;
-  if (c->fresh_steps > 0) c->fresh_steps--;
+  const bool risky = c->slab.on || c->fresh_steps > 0 || 2 * (int)c->hSt->list_used_f > c->cap_f ||
+                     2 * (int)c->hSt->list_used_b > c->cap_b || 2ull * c->hSt->list_used_d > c->cap_d;
+  if (!c->slab.on && c->fresh_steps > 0) c->fresh_steps--;
   if (!risky) return DFR_OK;
   for (int attempt = 0; attempt < 6; attempt++) {
     CU(cudaMemcpyAsync(c->hSt, c->dSt.p, sizeof(StepState), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->hSt->error_flags & ~7) break;  // a slab error: reported below, nothing to grow
     const int flags = c->hSt->error_flags & 7;
     if (!flags) return DFR_OK;
     const size_t nwarp = ((size_t)c->nf_cap + 31) / 32;

@@ -83,7 +83,7 @@ typedef struct dfr_config {
   /* Device-side tuning (0 = default).  These have no counterpart in the reference; they never change results.
    * The three capacities are INITIAL values: rows that do not fit make the context grow them and rebuild the lists
    * before the step continues (the reference's lists are unbounded); DFR_ERR_CAPACITY is only left for a row that
-   * more than doubles within one step outside the first steps after finalize / reset / load, and for slab contexts. */
+   * more than doubles within one step outside the first steps after finalize / reset / load. */
   int32_t neighbor_capacity_fluid;    /* fluid neighbours stored per fluid particle (default 96) */
   int32_t neighbor_capacity_boundary; /* boundary neighbours stored per fluid particle (default 64) */
   int32_t body_neighbor_capacity;     /* mean fluid neighbours stored per dynamic boundary particle (default 96) */
@@ -122,7 +122,8 @@ int dfr_set_init_v_omega(dfr_context *ctx, int body, const double v0[3], const d
  * which runs one OpenMP process).  Every rank builds the SAME scene (same dfr_set_fluid / dfr_add_body calls), then
  * calls dfr_slab_configure before dfr_finalize: the z cell layers are cut into n_ranks ranges of equal particle count,
  * the context keeps its range plus one support radius of ghost particles, and dfr_step exchanges boundary layers,
- * residuals, the CFL maximum and the per-body force/torque/Jacobian rows with NCCL (NVLink) on the context's stream.
+ * residuals, the CFL maximum and the per-body force/torque/Jacobian rows over NVLink on the context's stream (peer
+ * stores into cudaIpc-mapped neighbour memory; NCCL for setup, the steps after a reset, and as fallback).
  * id_bytes comes from dfr_slab_unique_id on rank 0 and is distributed by the caller (torch.distributed, MPI, a file).
  * Results equal the single-context run up to summation order.  Parity dumps (dfr_download_fluid) write only the ids a
  * rank owns; rigid bodies are replicated.  Not available with emitters or the rigid contact solver. */
@@ -180,10 +181,12 @@ int dfr_set_gradient_mode(dfr_context *ctx, int mode);
  * used instead: in the first four steps after finalize / reset / load (the neighbour-list capacities are being
  * watched), with the rigid contact solver once every 500 steps (the reference's z-sort of the contact order runs on the
  * host), while per-kernel profiling is on, and with DFR_NO_GRAPH=1.
- * Slab-decomposed contexts (peer-memory transport): k_begin_step and the particle exchange - NCCL transfers whose sizes the
- * host reads back, two synchronisations - stay on the stream, everything from the list build on is one graph replay per
- * step; residual sums, the CFL maximum and the per-body rows are all-reduced by small kernels over peer-mapped mailboxes
- * (no collective calls inside the solves).  With DFR_SLAB_TRANSPORT=nccl the round-1 stream path is used. */
+ * Slab-decomposed contexts (peer-memory transport) step the same way: one graph replay per step, nothing read back in
+ * between.  The particle exchange at the head of the step stores the export layers straight into the neighbours'
+ * receive areas and orders them with two flag passes; residual sums, the CFL maximum and the per-body rows are
+ * all-reduced by small kernels over peer-mapped mailboxes (no collective call, no host read-back inside a step).
+ * DFR_SLAB_HOST_EXCHANGE=1 keeps the NCCL particle exchange with its two read-backs at the head of every step,
+ * DFR_SLAB_TRANSPORT=nccl the whole round-1 stream path (the variables must be set on all ranks alike). */
 int dfr_step(dfr_context *ctx, int n_steps);
 
 /* Runs steps until TimeStepDiffDFSPH::is_trajectory_finish_callback() would be true

@@ -27,6 +27,7 @@ def main():
     manager = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     burst = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # then `bursts` calls of dfr_step(burst)
     bursts = int(sys.argv[5]) if len(sys.argv) > 5 else (2 if burst else 0)
+    row_capacity = int(sys.argv[6]) if len(sys.argv) > 6 else 0  # initial ELL row capacities (0: defaults); small values make the lists grow
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")  # control plane only (id broadcast, merging the parity dumps)
@@ -35,6 +36,8 @@ def main():
         sc["bodies"][b]["init_v"] = (0.3 * b, -0.2, 0.1)
         sc["bodies"][b]["init_omega"] = (0.5, 1.0 * b, -0.4)
     kw = dict(surface_tension_method=2, surface_tension=0.2, max_error=0.05, target_time=10.0, use_rigid_gradient_manager=manager)
+    if row_capacity:
+        kw.update(neighbor_capacity_fluid=row_capacity, neighbor_capacity_boundary=max(8, row_capacity // 2))
 
     def factory(**k):
         ctx = Context(device=local, **k)

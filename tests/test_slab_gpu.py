@@ -16,9 +16,10 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _run(n_particles, steps, manager, port, env_extra=None, burst=0, ranks=2):
+def _run(n_particles, steps, manager, port, env_extra=None, burst=0, ranks=2, row_capacity=0):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_check.py"), str(n_particles), str(steps), str(manager), str(burst)]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_check.py"), str(n_particles), str(steps), str(manager), str(burst),
+           "2", str(row_capacity)]
     env = dict(os.environ)
     env.update(env_extra or {})
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -38,12 +39,14 @@ def test_two_slabs_equal_one_domain(manager, transport):
          {"DFR_SLAB_TRANSPORT": "nccl"} if transport == "nccl" else None)
 
 
-@pytest.mark.parametrize("exchange", ["device", "host"])
+@pytest.mark.parametrize("exchange", ["device", "host", "device-small-rows"])
 def test_replayed_slab_steps_equal_one_domain(exchange):
     """16 single steps (reset after 8, state load after 9: steps 5-8 and 14-16 are graph replays) and then two calls of
     dfr_step(5), i.e. replays back to back with nothing read back in between.  exchange: the particle exchange at the head
     of a replayed step over peer memory inside the graph (default) or by NCCL with two host read-backs
-    (DFR_SLAB_HOST_EXCHANGE=1)."""
+    (DFR_SLAB_HOST_EXCHANGE=1); "device-small-rows" starts with ELL rows of 24 fluid / 12 boundary neighbours, so that the
+    lists have to grow both on the stream path (rebuild inside the step) and between replayed steps."""
     if _gpus() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    _run(30000, 16, 1, 29531 + (1 if exchange == "host" else 0), {"DFR_SLAB_HOST_EXCHANGE": "1"} if exchange == "host" else None, burst=5)
+    _run(30000, 16, 1, 29531 + ["device", "host", "device-small-rows"].index(exchange),
+         {"DFR_SLAB_HOST_EXCHANGE": "1"} if exchange == "host" else None, burst=5, row_capacity=24 if exchange.endswith("rows") else 0)
