@@ -67,7 +67,8 @@ class Config(C.Structure):
         ("neighbor_capacity_boundary", C.c_int32),
         ("body_neighbor_capacity", C.c_int32),
         ("grid_reach", C.c_int32),
-        ("reserved_i", C.c_int32 * 3),
+        ("use_release_rigid_body_mode", C.c_int32),
+        ("reserved_i", C.c_int32 * 2),
         ("reserved_d", C.c_double * 8),
     ]
 

@@ -1885,6 +1885,7 @@ int dfr_finalize(dfr_context *c) {
   P.gradient_mode = cfg.gradient_mode; P.rigid_body_mode = cfg.rigid_body_mode; P.optimize_rotation = cfg.optimize_rotation;
   P.use_manager = cfg.use_rigid_gradient_manager; P.use_contact = cfg.use_rigid_contact_solver;
   P.target_time = cfg.target_time; P.uniform_acc_time = cfg.uniform_acc_rb_time;
+  P.release_mode = cfg.use_release_rigid_body_mode != 0;
   P.time_step_size0 = cfg.time_step_size;
   P.n_bodies = (int)c->bodies.size();
   // ---- boundary layout: static bodies first, then dynamic ----

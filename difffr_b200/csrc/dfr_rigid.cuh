@@ -27,8 +27,22 @@ __global__ void k_begin_step(const __grid_constant__ Params P, StepState *st, Bo
   }
   if (b < P.n_bodies) {
     BodyDev &B = bodies[b];
-    if (B.dynamic) {
-      const double T = P.uniform_acc_time;
+    const double T = P.uniform_acc_time;
+    if (B.dynamic && P.release_mode) {
+      // :381-407: only boundary model 1 (the acting body) is touched - held at rest, then released; the reference sets its
+      // velocities back to the initial ones at the start of EVERY later step, and so does this
+      if (b == 1) {
+        if (st->time <= T + st->h) {
+          if (T > 1e-3) B.animated = 1;
+          B.vel = mk3(0.0, 0.0, 0.0);
+          B.omega = mk3(0.0, 0.0, 0.0);
+        } else {
+          B.vel = B.init_v;
+          B.omega = B.init_omega;
+          B.animated = 0;
+        }
+      }
+    } else if (B.dynamic) {
       if (st->time <= T + st->h) {
         double factor = 1.0;
         if (T > 1e-3) {

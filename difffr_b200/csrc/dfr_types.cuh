@@ -37,6 +37,7 @@ struct Params {
   double viscosity, viscosity_b, surface_tension, surface_tension_b;
   int gradient_mode, rigid_body_mode, optimize_rotation, use_manager, use_contact;
   double target_time, uniform_acc_time;
+  int release_mode;  // useReleaseRigidBodyMode (TimeStepDiffDFSPH.cpp:381-407)
   double time_step_size0;
   int n_bodies, n_dyn_bodies;
   int slab;                // slab-decomposed context: residual sums and body accumulators are all-reduced between kernels

@@ -250,6 +250,7 @@ inline Scene load_scene(const std::string &scene_file, const std::string &param 
     if (cfg->read("useRigidContactSolver", b)) c.use_rigid_contact_solver = b;
     if (cfg->read("useRigidGradientManager", b)) c.use_rigid_gradient_manager = b;
     cfg->read("useReleaseRigidBodyMode", sc.use_release_rigid_body_mode);
+    c.use_release_rigid_body_mode = sc.use_release_rigid_body_mode ? 1 : 0;
     cfg->read("rigidContactGamma", c.rigid_contact_gamma);
     cfg->read("rigidContactBeta", c.rigid_contact_beta);
     cfg->read("rigidContactSupportRadiusFactor", c.rigid_contact_support_radius_factor);

@@ -193,8 +193,6 @@ class SimulatorBase {
   void initSimulation() {
     if (ctx) throw std::runtime_error("initSimulation called twice");
     scene = load_scene(scene_file, param_str);
-    if (scene.use_release_rigid_body_mode)
-      throw std::runtime_error("useReleaseRigidBodyMode (billiards scenes) is outside the accelerated path");
     build_context();
     Simulation::current = &simulation;
     TimeManager::current = &time_manager;

@@ -88,7 +88,11 @@ typedef struct dfr_config {
   int32_t neighbor_capacity_boundary; /* boundary neighbours stored per fluid particle (default 64) */
   int32_t body_neighbor_capacity;     /* mean fluid neighbours stored per dynamic boundary particle (default 96) */
   int32_t grid_reach;                 /* cell edge = support radius / grid_reach, stencil (2 reach + 1)^3 (default 2) */
-  int32_t reserved_i[3];
+  /* "useReleaseRigidBodyMode" (billiards-on-water scenes; TimeStepDiffDFSPH.cpp:381-407): the velocity ramp is off; body 1
+   * is held at rest (animated) until uniformAccelerateRBTime has passed and from then on STARTS every step with its
+   * initial velocities; all other dynamic bodies move freely from t = 0. */
+  int32_t use_release_rigid_body_mode;
+  int32_t reserved_i[2];
   double reserved_d[8];
 } dfr_config;
 

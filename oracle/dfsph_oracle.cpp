@@ -1433,6 +1433,19 @@ void beginStep(dfr_context *c) {
   for (auto &b : c->bodies) {
     if (!b.dynamic) continue;
     const double T = c->cfg.uniform_acc_rb_time;
+    if (c->cfg.use_release_rigid_body_mode) {  // :381-407: only boundary model 1 is touched
+      if (&b != &c->bodies[1]) continue;
+      if (c->time <= T + c->h) {
+        if (T > 1e-3) b.animated = true;
+        b.vel = Vec3::zero();
+        b.omega = Vec3::zero();
+      } else {
+        b.vel = b.init_v;
+        b.omega = b.init_omega;
+        b.animated = false;
+      }
+      continue;
+    }
     if (c->time <= T + c->h) {
       double factor = 1.;
       if (T > 1e-3) {

@@ -331,7 +331,7 @@ int ref_finalize(dfr_context *c) {
   scene.timeStepSize = cfg.time_step_size;
   scene.useRigidContactSolver = cfg.use_rigid_contact_solver != 0;
   scene.useRigidGradientManager = cfg.use_rigid_gradient_manager != 0;
-  scene.useReleaseRigidBodyMode = false;
+  scene.useReleaseRigidBodyMode = cfg.use_release_rigid_body_mode != 0;
   scene.rigidContactGamma = cfg.rigid_contact_gamma;
   scene.rigidContactFrictionCoeff = cfg.rigid_contact_friction;
   scene.rigidContactBeta = cfg.rigid_contact_beta;

@@ -35,6 +35,19 @@ CASES = {
                                                                                            target_time=0.05, viscosity=0.02, viscosity_boundary=0.3,
                                                                                            gradient_mode=0), dict(steps=6, init_v=(0.6, -0.4, 0.2),
                                                                                                                   init_omega=(1.0, -2.0, 0.5))),
+    # useReleaseRigidBodyMode (billiards-on-water-2balls.json; TimeStepDiffDFSPH.cpp:381-407): body 1 is held until the ramp
+    # time has passed and then starts every step with its initial velocities, body 2 moves freely from t = 0
+    "release_mode_2box": (dict(n_target=1500, n_boxes=2, jitter=0.2, seed=9), dict(surface_tension_method=2, surface_tension=0.2, max_error=0.05,
+                                                                                     uniform_acc_rb_time=0.004, target_time=0.02,
+                                                                                     use_release_rigid_body_mode=1, use_rigid_gradient_manager=1),
+                          dict(steps=10, init_v=(0.8, -0.5, 0.1), init_omega=(1.0, 2.0, -0.5))),
+    # the billiards configuration itself: no ramp time, contact solver and gradient manager on
+    "release_mode_contact": (dict(n_target=1500), dict(surface_tension_method=2, surface_tension=0.2, max_error=0.05, target_time=0.05,
+                                                       uniform_acc_rb_time=0.0, use_release_rigid_body_mode=1, use_rigid_gradient_manager=1,
+                                                       use_rigid_contact_solver=1, rigid_contact_beta=20000.0),
+                             # (with init_v = (0.5, -0.3, 0.2) step 5 of this scene sits on a discontinuity of the contact Jacobian: the reference's own
+                             # blocks then differ by 16 % between 3 and 16 OpenMP threads; these velocities are clear of it)
+                             dict(steps=8, scene="contact", init_v=(0.3, -0.2, 0.1), init_omega=(0.4, 0.8, -0.3))),
     # penalty rigid-rigid contact + friction + manager (BASELINE.json configs[2]); reset() after step 4 exercises the
     # history-dependent contact order of the reference (oracle/oracle_contact.inc)
     "contact_manager_2box": (dict(n_target=1500), dict(surface_tension_method=2, surface_tension=0.3, max_error=0.05, target_time=0.05,

@@ -15,7 +15,7 @@ PAPER_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob
 FLUID_FIELDS = ["position", "velocity", "density", "factor", "kappa", "kappa_v", "density_adv", "acceleration", "sum_grad_p_k"]
 INT_KEYS = {"cfl_method", "min_iterations", "max_iterations", "max_iterations_v", "enable_divergence_solver", "use_pressure_warmstart",
             "use_divergence_warmstart", "viscosity_method", "surface_tension_method", "gradient_mode", "rigid_body_mode", "optimize_rotation",
-            "use_rigid_gradient_manager", "use_rigid_contact_solver", "max_emitted_particles"}
+            "use_rigid_gradient_manager", "use_rigid_contact_solver", "max_emitted_particles", "use_release_rigid_body_mode"}
 
 
 def load(name):
