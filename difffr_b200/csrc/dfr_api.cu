@@ -767,6 +767,20 @@ int slab_p2p_setup(dfr_context *c) {
   const char *env = getenv("DFR_SLAB_TRANSPORT");
   int want = !(env && std::string(env) == "nccl");
   CU(S.flags.alloc(8));
+  {
+    // Receive area of the device-side particle exchange.  A sender addresses rows in the RECEIVER's layout, so every
+    // rank uses the same row capacity: the largest send_cap of the job (the estimates differ from slab to slab; with
+    // per-rank capacities the velocity / misc rows landed at the wrong offsets - found by the 4- and 8-rank slab checks).
+    int cap = S.send_cap;
+    CU(cudaMemcpyAsync(S.counts.p, &cap, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(N->AllReduce(S.counts.p, S.counts.p, 1, ncclInt, ncclMax, S.comm, c->stream));
+    CU(cudaMemcpyAsync(&cap, S.counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    S.xin.free();
+    CU(S.xin.alloc(xchg_bytes(cap)));
+    S.xchg.mine = S.xin.p;
+    S.xchg.cap = cap;
+  }
   const int NH = 7;
   CU(S.ipc_stage.alloc(3 * NH * sizeof(cudaIpcMemHandle_t) + 16));
   void *mine[NH] = {c->xk.p, c->xrho.p, c->normal.p, c->vel[0].p, c->vel[1].p, S.flags.p, S.xin.p};
@@ -1001,12 +1015,12 @@ int slab_exchange_device(dfr_context *c) {
   double4 *nul = nullptr;
   CU(cudaMemsetAsync(S.counts.p, 0, 8 * sizeof(int), c->ls));
   LAUNCH(c, k_slab_select, gcap, 128, c->P, S.G, st, c->pos[a].p, c->vel[c->vcur].p, c->kappa[a].p, c->kappav[a].p, c->pid[a].p,
-         c->pstate[a].p, S.send_cap, X.peer_lo ? xchg_rows(X.peer_lo, 1, 0, X.cap) : nul, X.peer_lo ? xchg_rows(X.peer_lo, 1, 1, X.cap) : nul,
+         c->pstate[a].p, X.cap, X.peer_lo ? xchg_rows(X.peer_lo, 1, 0, X.cap) : nul, X.peer_lo ? xchg_rows(X.peer_lo, 1, 1, X.cap) : nul,
          X.peer_lo ? xchg_rows(X.peer_lo, 1, 2, X.cap) : nul, X.peer_hi ? xchg_rows(X.peer_hi, 0, 0, X.cap) : nul,
          X.peer_hi ? xchg_rows(X.peer_hi, 0, 1, X.cap) : nul, X.peer_hi ? xchg_rows(X.peer_hi, 0, 2, X.cap) : nul, S.counts.p, &st->error_flags);
   LAUNCH(c, k_slab_xchg_post_rows, 1, 32, S.counts.p, X, flo, fhi, (volatile unsigned long long *)S.flags.p, S.seq.p + 0, 5000000000ull,
          &st->error_flags);
-  LAUNCH(c, k_slab_xchg_unpack, std::max(1, cdiv(2 * (int64_t)S.send_cap, 128)), 128, st, X, (int)c->nf_cap, c->pos[a].p, c->vel[c->vcur].p,
+  LAUNCH(c, k_slab_xchg_unpack, std::max(1, cdiv(2 * (int64_t)X.cap, 128)), 128, st, X, (int)c->nf_cap, c->pos[a].p, c->vel[c->vcur].p,
          c->kappa[a].p, c->kappav[a].p, c->pid[a].p, c->pstate[a].p);
   // sort [own_begin, own_end + received) by (cell, id) into the other buffers
   CU(cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->ls));
@@ -2031,10 +2045,7 @@ int dfr_finalize(dfr_context *c) {
     }
     CU(S.r_misc.alloc(2 * (size_t)S.send_cap));
     CU(S.counts.alloc(8));
-    CU(S.xin.alloc(xchg_bytes(S.send_cap)));
-    std::memset(&S.xchg, 0, sizeof(S.xchg));
-    S.xchg.mine = S.xin.p;
-    S.xchg.cap = S.send_cap;
+    std::memset(&S.xchg, 0, sizeof(S.xchg));  // the receive area is sized in slab_p2p_setup (one capacity for all ranks)
     S.xchg_ok = false;
     CU(S.body_buf.alloc(std::max<size_t>(c->bodies.size(), 1) * ACC_N));
     if (cudaMallocHost((void **)&S.h_counts, 8 * sizeof(int)) != cudaSuccess) return fail(c, DFR_ERR_CUDA, "cudaMallocHost");

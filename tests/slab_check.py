@@ -57,7 +57,10 @@ def main():
     def advance_and_compare(s, k):
         """k steps in one dfr_step call on both sides (k > 1: replayed steps back to back, nothing read back in between)"""
         nonlocal worst
-        slab.step(k)
+        try:
+            slab.step(k)
+        except Exception as e:
+            raise RuntimeError(f"rank {rank}: slab step {s} (x{k}) failed: {e}") from e
         info = slab.step_info()
         owned = torch.tensor([info.num_fluid_particles], dtype=torch.int64)
         dist.all_reduce(owned)
@@ -125,4 +128,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failing rank must take the job down at once: the others would wait in a collective
+        import traceback
+
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
