@@ -307,6 +307,7 @@ PYBIND11_MODULE(_core, m) {
     d["gradient_mode"] = sc.cfg.gradient_mode;
     d["max_error"] = sc.cfg.max_error;
     d["use_rigid_contact_solver"] = sc.cfg.use_rigid_contact_solver;
+    d["use_release_rigid_body_mode"] = sc.cfg.use_release_rigid_body_mode;
     py::list bodies;
     for (const BodyDesc &b : sc.bodies) {
       py::dict bd;

@@ -44,6 +44,11 @@ SCENES = {
     # emitter firing in the first step, Akinci-2013 surface tension on).  The body samples are rounded to float32 before
     # BOTH sides use them, which halves the fixture (3.4 MB of the file are those samples).
     "paper_high_diving": ("diff-high-diving-duck.json", None, 6, {"paper": {}}, 6),
+    # the fifth paper scene (not in BASELINE.json's configs): billiards on water - two dynamic balls, penalty contact solver,
+    # gradient manager, useReleaseRigidBodyMode (ball 1 is held for the first steps and then starts EVERY step with its
+    # initial velocity, TimeStepDiffDFSPH.cpp:381-407), with the shipped fluid state state/billiards/state_17 (87,374
+    # particles, float32 on disk and in the fixture; body samples rounded to float32 as for high diving)
+    "paper_billiards": ("billiards-on-water-2balls.json", "billiards/state_17_particle_Fluid.bgeo", 12, {"paper": {}}, 12),
     # (five steps of state, two of sensitivities: the bunny starts inside a perfect lattice whose particles all have
     # rho* = 1 up to rounding, i.e. they sit ON the rho* > 1 gate of the Jacobians (TimeStepDiffDFSPH.cpp:1539).  Which side
     # a particle falls on is rounding noise, so from the third step on the net Jacobians of any two FP-different runs (the
@@ -51,6 +56,7 @@ SCENES = {
     # of configs[0] only reaches the water after several hundred steps and its settled state is not in the reference
     # repository: no golden for it.)
 }
+F32_FIXTURE = {"paper_high_diving", "paper_billiards"}  # body samples (and a float32 state file's arrays) stored as float32
 FLUID_FIELDS = ["position", "velocity", "kappa", "density_adv"]
 FLUID_STRIDE = 32  # recorded for every 32nd particle (fixture size)
 FLUID_STEP = 8  # fluid fields are recorded after this step (later the sloshing fluid has amplified rounding differences too far)
@@ -65,7 +71,7 @@ def run_segment(name, seg):
 
     sph = import_sph()
     sc = sph._load_scene_full(SCENE, "")
-    if name == "paper_high_diving":
+    if name in F32_FIXTURE:
         for bd in sc["bodies"]:
             bd["samples"] = bd["samples"].astype(np.float32).astype(np.float64)
     st = sph._read_bgeo(os.path.join(REF, "state", state_file)) if state_file else None
@@ -93,7 +99,10 @@ def run_segment(name, seg):
         out.update({"config_bytes": np.frombuffer(sc["config"], dtype=np.uint8), "fluid_x": sc["fluid_x"], "fluid_v": sc["fluid_v"],
                     "n_bodies": len(sc["bodies"]), "steps": STEPS, "grad_steps": GRAD_STEPS, "fluid_step": min(FLUID_STEP, STEPS), "fluid_stride": FLUID_STRIDE, "segments": np.array(list(SEGMENTS.keys()))})
         if st is not None:
-            out.update({"state_x": st["x"], "state_v": st["v"], "state_kappa": st["kappa"], "state_kappa_v": st["kappa_v"]})
+            f32 = name in F32_FIXTURE
+            for k in ("x", "v", "kappa", "kappa_v"):
+                assert not f32 or np.array_equal(st[k].astype(np.float32).astype(np.float64), st[k]), "state file is not float32"
+                out["state_" + k] = st[k].astype(np.float32) if f32 else st[k]
         out["n_emitters"] = len(sc["emitters"])
         for k, e in enumerate(sc["emitters"]):
             out[f"emitter{k}_wh"] = np.array([e["width"], e["height"]])
@@ -101,7 +110,7 @@ def run_segment(name, seg):
             out[f"emitter{k}_rotation"] = np.asarray(e["rotation"], dtype=np.float64)
             out[f"emitter{k}_vse"] = np.array([e["velocity"], e["emit_start"], e["emit_end"]], dtype=np.float64)
         for i, b in enumerate(sc["bodies"]):
-            out[f"body{i}_samples"] = b["samples"].astype(np.float32) if name == "paper_high_diving" else b["samples"]
+            out[f"body{i}_samples"] = b["samples"].astype(np.float32) if name in F32_FIXTURE else b["samples"]
             out[f"body{i}_dynamic"] = int(b["dynamic"])
             out[f"body{i}_density"] = float(b["density"])
             out[f"body{i}_translation"] = b["translation"]

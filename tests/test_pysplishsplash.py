@@ -97,6 +97,9 @@ def test_scene_loader_rejects_what_is_outside_the_path(tmp_path):
     with pytest.raises(RuntimeError, match="isAnimated"):
         sph._load_scene_summary(path)
     sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"sim2D": False}))  # the 3-D default spelled out is fine
+    # the billiards scenes' start-up variant is part of the path (TimeStepDiffDFSPH.cpp:381-407; goldens release_mode_*)
+    assert sph._load_scene_summary(write_scene(tmp_path, extra_cfg={"useReleaseRigidBodyMode": True}))["use_release_rigid_body_mode"] == 1
+    assert sph._load_scene_summary(write_scene(tmp_path))["use_release_rigid_body_mode"] == 0
 
 
 def test_no_cpu_fallback(tmp_path):
@@ -161,3 +164,15 @@ def test_paper_scenes_load_with_the_reference_particle_counts(scene, n_fluid, n_
     assert len(d["bodies"]) == n_bodies and d["num_emitters"] == n_emitters
     assert all(b["num_particles"] > 100 for b in d["bodies"])
     assert sum(1 for b in d["bodies"] if b["dynamic"]) == 1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="the reference checkout is only present in the build container")
+def test_billiards_scene_loads_with_the_particle_count_of_its_shipped_state():
+    """The fifth paper scene: two dynamic balls, contact solver, gradient manager, useReleaseRigidBodyMode; the lattice has
+    exactly the particle count of state/billiards/state_17_particle_Fluid.bgeo (golden: paper_billiards)."""
+    sph = import_sph()
+    d = sph._load_scene_summary(os.path.join(REF_SCENES, "billiards-on-water-2balls.json"))
+    st = sph._read_bgeo(os.path.join(os.path.dirname(REF_SCENES), "state", "billiards", "state_17_particle_Fluid.bgeo"))
+    assert d["num_fluid"] == st["n"] == 87374
+    assert [b["dynamic"] for b in d["bodies"]] == [False, True, True]
+    assert d["use_release_rigid_body_mode"] == 1 and d["use_rigid_contact_solver"] == 1
