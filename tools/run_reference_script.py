@@ -7,9 +7,10 @@
           - a git-ignored scratch directory that only exists to carry the files to the GPU box (the reference checkout
           does not exist there); delete it after the run.  Nothing of it is committed.
   optimise (GPU box):
-      python tools/run_reference_script.py optimise stone|water [out_dir]
+      python tools/run_reference_script.py optimise stone|water|billiards [out_dir]
           the README's command for that task (README.md:62-78) with a bounded --maxIter: stone skipping (BASELINE.json
-          configs[0]) for one gradient iteration on the regenerated settled state; water rafting (configs[1]) with Adam,
+          configs[0]) for one gradient iteration on the regenerated settled state; billiards (README.md:84-87, the
+          reference's diff-rigid-contact-multi.py on the shipped state_17) for four iterations; water rafting (configs[1]) with Adam,
           lr 0.1 as in the authors' log (raw_record_and_plot/water_rafting/2023-05-14-dambreak-bunny-ours) for 25 iterations
           after settling its fluid on the GPU.  Loss per iteration and wall time go to reference_script_<task>.json.
   run (GPU box):
@@ -37,7 +38,8 @@ REF = "/root/reference/experiments/rigid_body_trajectory_optimization"
 FILES = ["python/gradient-based-optimize.py", "python/utils.py", "scene/diff-bottle-model-collide.json", "scene/diff-stone-skipping.json",
          "scene/diff-water-rafting-bunny.json", "models/UnitBox.obj", "models/bottle.obj", "models/sphere.obj", "models/bunny-fix.obj",
          "state/bottle_flip/state_54.bin", "state/bottle_flip/state_54_particle_Fluid.bgeo", "state/stone_skipping/state_18.bin",
-         "state/water_rafting/state_130.bin"]
+         "state/water_rafting/state_130.bin", "python/diff-rigid-contact-multi.py", "scene/billiards-on-water-2balls.json",
+         "state/billiards/state_17.bin", "state/billiards/state_17_particle_Fluid.bgeo"]
 # the README's commands (README.md:62-78) with a bounded number of optimiser iterations
 TASKS = {
     "bottle": dict(scene="diff-bottle-model-collide.json", state="bottle_flip/state_54.bin", args=["--taskType", "bottle-flip", "--maxIter", "0"]),
@@ -46,6 +48,10 @@ TASKS = {
     "water": dict(scene="diff-water-rafting-bunny.json", state="water_rafting/state_130.bin",
                   args=["--load-fluid-pos-and-vel", "--taskType", "water-rafting", "--optimizer", "adam", "--lr-v", "0.1", "--lr-omega", "0.1",
                         "--patience", "10", "--maxIter", "24"]),
+    # README.md:84-87: on-water billiards with the reference's OTHER script (two dynamic balls, contact solver, gradient
+    # manager blocks across bodies, useReleaseRigidBodyMode) on the shipped state_17, Adam as coded in the script
+    "billiards": dict(script="diff-rigid-contact-multi.py", scene="billiards-on-water-2balls.json", state="billiards/state_17.bin",
+                      args=["--load-fluid-pos", "--maxIter", "3"]),
 }
 
 
@@ -83,7 +89,7 @@ def numbers(text):
 def run_script(task, out_dir):
     os.makedirs(out_dir, exist_ok=True)
     T = TASKS[task]
-    script = os.path.join(STAGE, "python", "gradient-based-optimize.py")
+    script = os.path.join(STAGE, "python", T.get("script", "gradient-based-optimize.py"))
     scene = os.path.join(STAGE, "scene", T["scene"])
     state = os.path.join(STAGE, "state", T["state"])
     env = dict(os.environ)
@@ -97,7 +103,8 @@ def run_script(task, out_dir):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
     wall = time.time() - t0
     open(os.path.join(out_dir, "script_stdout.txt"), "w").write(" ".join(cmd) + "\n" + r.stdout + "\n---- stderr ----\n" + r.stderr)
-    log = open(os.path.join(sim_out, "log", "SPH_log.txt")).read()
+    log_path = os.path.join(sim_out, "log", "SPH_log.txt")
+    log = open(log_path).read() if os.path.exists(log_path) else ""
     log = re.compile(r"\x1b\[[0-9;]*m").sub("", log)
     open(os.path.join(out_dir, "SPH_log.txt"), "w").write(log)
     return r, log, wall, scene
@@ -114,6 +121,8 @@ def run_optimisation(task, out_dir):
     r, log, wall, _ = run_script(task, out_dir)
     losses = [numbers(m)[0] for m in re.findall(r"\bloss = ([^\n]*)", log)]
     losses = losses[:: 2] if task != "stone" else losses  # two layers (v, omega) log the same loss once each per iteration
+    if task == "billiards":  # this script prints its loss ("===== iter k, loss = [tensor([...])] ====") instead of logging it
+        losses = [numbers(m)[0] for m in re.findall(r"iter \d+, loss = \[tensor\(\[([^\]]*)\]", r.stdout)]
     steps = [int(numbers(m)[0]) for m in re.findall(r"total timestep of a trajectory = ([^\n]*)", log)]
     grads = re.findall(r"(grad_[a-z_]+ = \[[^\]]*\])", log)
     res = {"task": task, "command_args": TASKS[task]["args"], "script_exit_code": r.returncode, "wall_seconds": wall, "iterations": len(losses),
