@@ -515,7 +515,8 @@ int sync_state(dfr_context *c) {
 // and the whole step hangs in an IF node opened by k_step_gate, so that dfr_run_trajectory can enqueue steps in batches
 // without looking at `finished` after every one.  Nothing in a replayed step needs the host: no speculation, no
 // read-back between the solves.
-// Not recorded (the stream path below stays): slab-decomposed contexts (NCCL calls and host-side exchange sizes),
+// Not recorded (the stream path below stays): slab-decomposed contexts on the NCCL transport (collective calls and
+// host-side exchange sizes; with the peer-memory transport a slab step is recorded like any other, slab_exchange_device),
 // per-kernel profiling, steps in which the list capacities are being watched, DFR_NO_GRAPH=1.
 #define CUG(call)                                                                                        \
   do {                                                                                                   \
