@@ -131,7 +131,11 @@ struct dfr_context {
   int n_acc_blocks = 0;
 
   // grids
-  DevBuf<unsigned int> cell_start_f, cell_start_s, cell_start_d, tile_sums;
+  DevBuf<unsigned int> cell_start_f, cell_start_s, cell_start_d, tile_sums, tile_sums_side;
+  // recorded steps: the grid of the dynamic boundary particles is built on a side branch of the graph, next to the sort of the fluid
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool on_side_branch = false;
   DevBuf<unsigned char> near_s;  // per cell: a static boundary particle may be within reach (k_mark_near, marked once)
   DevBuf<unsigned char> near_d;  // the same for the dynamic boundary particles, re-marked with their cell table
   DevBuf<int> cell_of_p, rank_in_cell, sorted_src_f, sorted_src_d, cell_of_b, rank_b;
@@ -331,9 +335,10 @@ int persistent_grid(dfr_context *c, K kernel, int nvb) {
 int scan_u32(dfr_context *c, unsigned int *data, size_t n, unsigned int *total) {
   const int ntiles = cdiv((int64_t)n, SCAN_TILE);
   if ((size_t)ntiles > c->tile_sums.n) return fail(c, DFR_ERR_CAPACITY, "scan scratch too small");
-  LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, data, data, c->tile_sums.p, n);
-  LAUNCH(c, k_scan_sums, 1, 1024, c->tile_sums.p, ntiles, total);
-  if (ntiles > 1) LAUNCH(c, k_scan_add, cdiv((int64_t)n, 1024), 256, data, c->tile_sums.p, n);
+  unsigned int *ts = c->on_side_branch ? c->tile_sums_side.p : c->tile_sums.p;  // two scans may be in flight in a recorded step
+  LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, data, data, ts, n);
+  LAUNCH(c, k_scan_sums, 1, 1024, ts, ntiles, total);
+  if (ntiles > 1) LAUNCH(c, k_scan_add, cdiv((int64_t)n, 1024), 256, data, ts, n);
   return DFR_OK;
 }
 
@@ -436,7 +441,7 @@ int build_dyn_grid(dfr_context *c) {
   return DFR_OK;
 }
 
-int build_neighbor_lists(dfr_context *c);
+int build_neighbor_lists(dfr_context *c, bool dyn_grid_done = false);
 int slab_exchange_and_sort(dfr_context *c);
 int slab_exchange_device(dfr_context *c);
 // CompactNSearch replacement: counting sort of the fluid into cell order + neighbour lists
@@ -450,6 +455,26 @@ int build_neighbors(dfr_context *c) {
     return build_neighbor_lists(c);
   }
   const int a = c->cur, b = 1 - c->cur;
+  // Recorded steps: the grid of the dynamic boundary particles (8 small launches, independent of the fluid's sort) goes on
+  // a side branch of the graph - fork here, join in front of the list build (DFR_NO_FORK=1: one chain as on the stream).
+  const bool fork = c->capturing && c->n_dyn_p > 0 && getenv_int("DFR_NO_FORK") == 0;
+  cudaStream_t main_stream = c->ls;
+  if (fork) {
+    if (!c->side_stream) {
+      CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->ev_fork, main_stream));
+    CU(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    c->ls = c->side_stream;
+    c->on_side_branch = true;
+    int rcd = build_dyn_grid(c);
+    c->on_side_branch = false;
+    c->ls = main_stream;
+    if (rcd) return rcd;
+    CU(cudaEventRecord(c->ev_join, c->side_stream));
+  }
   cudaMemsetAsync(c->cell_start_f.p, 0, sizeof(unsigned int) * (nc + 1), c->ls);
   LAUNCH(c, k_bin_count, cdiv(n, 128), 128, c->P, c->pos[a].p, nf_ptr, 0, c->cell_start_f.p, c->cell_of_p.p, c->rank_in_cell.p);
   int rc = scan_u32(c, c->cell_start_f.p, (size_t)nc + 1, nullptr);
@@ -462,17 +487,28 @@ int build_neighbors(dfr_context *c) {
          c->pid[b].p, c->pstate[b].p);
   c->cur = b;
   c->vcur = 1 - c->vcur;
-  return build_neighbor_lists(c);
+  if (fork) CU(cudaStreamWaitEvent(c->ls, c->ev_join, 0));
+  return build_neighbor_lists(c, fork);
 }
 
 // neighbour lists of the sorted fluid (and the dynamic-boundary -> fluid rows)
-int build_neighbor_lists(dfr_context *c) {
+int build_neighbor_lists(dfr_context *c, bool dyn_grid_done) {
   const int n = c->launch_nf;
-  int rc = build_dyn_grid(c);
+  int rc = dyn_grid_done ? DFR_OK : build_dyn_grid(c);
   if (rc) return rc;
-  PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
-         c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
-         c->near_s.p, c->near_d.p);
+  // Recorded steps: the rows of the dynamic boundary particles (count, scan, fill: they only read the sorted fluid) are
+  // built on a side branch of the graph while k_nbr_build runs (dyn_grid_done says build_neighbors set the branch up).
+  const bool fork = dyn_grid_done && c->capturing && c->n_dyn_p > 0 && c->side_stream != nullptr;
+  cudaStream_t main_stream = c->ls;
+  if (fork) {
+    CU(cudaEventRecord(c->ev_fork, main_stream));
+    CU(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    c->ls = c->side_stream;
+    c->on_side_branch = true;
+  } else
+    PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+           c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
+           c->near_s.p, c->near_d.p);
   if (c->n_dyn_p > 0) {
     cudaMemsetAsync(c->off_d.p, 0, sizeof(unsigned int) * (c->n_dyn_p + 1), c->ls);
     LAUNCH(c, k_dnbr_count, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c), c->off_d.p);
@@ -480,6 +516,15 @@ int build_neighbor_lists(dfr_context *c) {
     if (rc) return rc;
     LAUNCH(c, k_dnbr_fill, cdiv((int64_t)c->n_dyn_p * 32, 128), 128, c->P, c->dSt.p, c->bpos.p, c->dyn_begin, c->n_dyn_p, grid_fluid(c),
            c->off_d.p, c->idx_d.p, c->cap_d);
+  }
+  if (fork) {
+    c->on_side_branch = false;
+    c->ls = main_stream;
+    CU(cudaEventRecord(c->ev_join, c->side_stream));
+    PLAUNCH(c, k_nbr_build, cdiv(n, 128), c->P, c->dSt.p, c->pos[c->cur].p, grid_fluid(c), grid_static(c), grid_dyn(c),
+           c->n_static_p > 0 ? 1 : 0, c->n_dyn_p > 0 ? 1 : 0, c->cnt_f.p, c->cnt_b.p, c->idx_f.p, c->idx_b.p, c->cap_f, c->cap_b,
+           c->near_s.p, c->near_d.p);
+    CU(cudaStreamWaitEvent(c->ls, c->ev_join, 0));
   }
   return DFR_OK;
 }
@@ -620,6 +665,7 @@ int capture_step_graph(dfr_context *c, int gated) {
   cudaGraph_t g = nullptr;
   e = cudaStreamEndCapture(c->cap_stream[0], &g);
   c->capturing = false;
+  c->on_side_branch = false;
   c->cap_target = nullptr;
   c->cap_counter = nullptr;
   c->ls = c->stream;
@@ -1687,6 +1733,9 @@ void dfr_destroy(dfr_context *c) {
   drop_step_graphs(c);
   for (auto &cs : c->cap_stream)
     if (cs) cudaStreamDestroy(cs);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (int k = 0; k < 2; k++) {
     c->pos[k].free(); c->vel[k].free(); c->kappa[k].free(); c->kappav[k].free(); c->pid[k].free(); c->pstate[k].free();
   }
@@ -1697,7 +1746,7 @@ void dfr_destroy(dfr_context *c) {
   c->blk_body.free(); c->blk_first.free(); c->cell_start_f.free(); c->cell_start_s.free(); c->cell_start_d.free();
   c->near_s.free();
   c->near_d.free();
-  c->tile_sums.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
+  c->tile_sums.free(); c->tile_sums_side.free(); c->cell_of_p.free(); c->rank_in_cell.free(); c->sorted_src_f.free(); c->sorted_src_d.free();
   c->cell_of_b.free(); c->rank_b.free(); c->cnt_f.free(); c->cnt_b.free(); c->idx_f.free(); c->idx_b.free(); c->idx_d.free();
   c->off_d.free(); c->dSt.free(); c->dEmitters.free();
   c->sched_ctr.free();
@@ -2090,6 +2139,7 @@ int dfr_finalize(dfr_context *c) {
   CU(cudaMemsetAsync(c->near_s.p, 0, (size_t)nc, c->stream));
   const size_t max_scan = std::max<size_t>((size_t)nc + 1, (size_t)c->n_dyn_p + 1);
   CU(c->tile_sums.alloc(max_scan / SCAN_TILE + 2));
+  CU(c->tile_sums_side.alloc(max_scan / SCAN_TILE + 2));
   CU(c->cell_of_p.alloc(N)); CU(c->rank_in_cell.alloc(N)); CU(c->sorted_src_f.alloc(N));
   const size_t ND = (size_t)std::max(c->n_dyn_p, 1), NS = (size_t)std::max(c->n_static_p, 1);
   CU(c->sorted_src_d.alloc(std::max(ND, NS))); CU(c->cell_of_b.alloc(std::max(ND, NS))); CU(c->rank_b.alloc(std::max(ND, NS)));
