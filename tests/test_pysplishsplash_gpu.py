@@ -114,7 +114,8 @@ def test_new_init_velocity_changes_the_trajectory_and_state_files_round_trip(tmp
     base.runNewTrajectory()
     x_b = bm.get_position_rb()
     assert x_b[0] - x_a[0] > 0.5 * (1.5 - 0.5) * 0.01  # the body travelled further in x
-    # finite-difference check of d x / d v0 against the propagated sensitivity (first column)
+    # finite-difference check of d x / d v0 against the propagated sensitivity (first column).  25 %: the reference's
+    # recurrence is itself that far from the derivative of the trajectory (tests/test_oracle_fd.py pins the gap on the oracle)
     gx = bm.get_grad_x_to_v0()
     fd = (x_b - x_a) / 1.0
     assert np.linalg.norm(fd - gx[:, 0]) < 0.25 * np.linalg.norm(gx[:, 0])
